@@ -1,0 +1,316 @@
+#!/usr/bin/env python
+"""Headline benchmark: env-steps/s for 65 536 batched CSTR envs per B200 (BASELINE.json config 3).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+One bench "step" = ONE pcg_rollout launch: all 65 536 envs of this GPU advanced through the 99 control
+intervals of an episode (N = 100), each interval = Tsit5 RK5(4) step of the CSTR ODE + Gaussian
+measurement noise + constraint flags + setpoint reward + observation normalisation (fp64).
+Weak scaling: every rank owns its own 65 536 envs (no collective on the step path).
+
+Prints ONE JSON line (rank 0).  Keys beyond the driver contract:
+  roofline      HBM roofline of the rollout kernel: algorithmic bytes / CUDA-event launch time
+  cpu_baseline  the restated reference step() on the host cores (bounded sample)
+  e2e           same metric through make_env.rollout() with pinned HOST buffers, copies in the timed region
+  step_mode     the Gym-style one-interval-per-launch path (launch-latency bound), for information
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+N_ENVS = 65536
+N_HORIZON = 100                      # reference N; an episode is N-1 = 99 steps (pcgym.py:448)
+K_STEPS = N_HORIZON - 1
+# algorithmic bytes per env-step actually moved by the headline configuration (DESIGN.md "Roofline"):
+#   read  a[1]                                   8
+#   write x_traj[2] obs[3] reward[1] g[2]       64
+#   write done, violated (u8)                    2
+# SURVEY 8(d) quotes 82 B because it assumes per-env setpoint tensors (8 B more read per env-step); the
+# headline uses the reference's shared setpoint schedule, which costs no per-env traffic.
+BYTES_PER_ENV_STEP = 74
+HEADLINE_INTEGRATOR = {"scheme": "tsit5", "adaptive": False, "n_sub": 1}
+
+
+def cstr_headline(n_envs=N_ENVS, device="cuda", seed=0, env_id0=0):
+    """env_params + actions [K, 1, n] for BASELINE config 3."""
+    import torch
+    g = torch.Generator(device="cpu").manual_seed(seed + 7919 * (env_id0 // max(n_envs, 1)))
+    jitter = 1 + 0.02 * (torch.rand(n_envs, 2, generator=g, dtype=torch.float64) * 2 - 1)
+    x0 = torch.cat([torch.tensor([0.8, 330.0], dtype=torch.float64) * jitter,
+                    torch.full((n_envs, 1), 0.85, dtype=torch.float64)], dim=1)
+    params = {
+        "model": "cstr", "N": N_HORIZON, "tsim": 25.0, "n_envs": n_envs, "device": device,
+        "SP": {"Ca": [0.85] * 50 + [0.9] * 50},
+        "o_space": {"low": np.array([0.7, 300.0, 0.8]), "high": np.array([1.0, 350.0, 0.9])},
+        "a_space": {"low": np.array([295.0]), "high": np.array([302.0])},
+        "x0": x0.to(device) if device != "cpu" else x0,
+        "r_scale": {"Ca": 1e3},
+        "noise": True, "noise_percentage": 0.001,
+        "constraints": lambda x, u: np.array([319 - x[1], x[1] - 331]).reshape(-1,),
+        "done_on_cons_vio": False, "r_penalty": True,
+        "constraint_units": "physical",
+        "integrator": dict(HEADLINE_INTEGRATOR),
+        "seed": seed, "env_id0": env_id0,
+    }
+    acts = torch.rand(K_STEPS, 1, n_envs, generator=g, dtype=torch.float64) * 2 - 1
+    return params, (acts.to(device) if device != "cpu" else acts)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx, self.rows, self.proc = gpu_index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.idx), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            self.thr = threading.Thread(target=self._pump, daemon=True)
+            self.thr.start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+        return self
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:  # noqa: BLE001
+                self.proc.kill()
+
+    def summary(self):
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 9:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------ reference arm
+def run_reference(args):
+    """`--impl reference`: the restated reference step() on the host cores (CasADi is not installable here)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import baseline
+    cores = len(os.sched_getaffinity(0))
+    per = max(1, args.ref_envs_per_worker)
+    for _ in range(max(args.warmup, 0) and 1):
+        baseline.run(envs_per_worker=1, n_steps=20, cores=cores)
+    vals, total, busy = [], 0, 0.0
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        r = baseline.run(envs_per_worker=per, cores=cores)
+        vals.append(r["value"])
+        total += r["env_steps"]
+    wall = time.perf_counter() - t0
+    value = float(np.mean(vals))
+    line = {
+        "impl": "reference", "metric": "env-steps/s", "value": value, "unit": "env-steps/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / max(args.steps, 1),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "CSTR config 3 (noise + constraints), restated reference step() one env per call, "
+                               "scipy LSODA 1e-6/1e-8 standing in for CasADi/CVODES (not installable offline)",
+                   "n_envs_sampled": per * cores, "episode_steps": K_STEPS},
+        "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": cores, "kind": "port",
+                         "sample": f"{args.steps} x ({cores} workers x {per} envs x {K_STEPS} steps)"},
+        "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------ our arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--n-envs", type=int, default=N_ENVS, help="envs per GPU")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ref-envs-per-worker", type=int, default=8)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+
+    # CPU baseline first (rank 0, N=1 only), before this process touches CUDA: workers are spawned
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import baseline
+        cpu = baseline.run(envs_per_worker=12)
+        cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+
+    import torch
+    import torch.distributed as dist
+    from pcgym_b200 import _native as nat
+    from pcgym_b200 import make_env, sharding
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (the engine has no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = f"cuda:{local}"
+    if world > 1:
+        sharding.init_from_env("nccl")
+    n = args.n_envs
+    W, K = max(args.warmup, 3), args.steps
+
+    params, acts0 = cstr_headline(n_envs=n, device=dev, seed=0, env_id0=rank * n)
+    env = make_env(params)
+    env.reset()
+    # ring of action buffers so consecutive launches never re-read the same (possibly L2-resident) input
+    ring = [acts0] + [(torch.rand_like(acts0) * 2 - 1) for _ in range(2)]
+    lib = nat.lib()
+
+    def one_rollout(i):
+        env.rewind()
+        return env.rollout(ring[i % len(ring)])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- resident-input throughput (`value`) + per-launch kernel time (roofline)
+    for i in range(W):
+        one_rollout(i)
+    barrier()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    t_all0, t_all1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0 = lib.pcg_launch_count()
+    with ClockSampler(local) as clk:
+        barrier()
+        t_all0.record()
+        for i in range(K):
+            ev[i][0].record()
+            one_rollout(i)
+            ev[i][1].record()
+        t_all1.record()
+        barrier()
+        launches = lib.pcg_launch_count() - l0
+        # keep the GPU busy a little longer so the 100 ms sampler sees the loaded clocks
+        t_end = time.perf_counter() + 0.6
+        while time.perf_counter() < t_end:
+            one_rollout(0)
+        torch.cuda.synchronize()
+    total_ms = t_all0.elapsed_time(t_all1)
+    kern_ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
+    total_ms = sharding.max_over_ranks(total_ms, dev)
+    kern_ms_max = sharding.max_over_ranks(kern_ms, dev)
+    env_steps_per_launch = n * K_STEPS
+    value = world * env_steps_per_launch * K / (total_ms * 1e-3)
+
+    # ---- end-to-end through the public API with HOST buffers (pinned): H2D actions, D2H obs/reward/done
+    a_host = [r.cpu().pin_memory() for r in ring[:2]]
+    out_host = None
+    def one_e2e(i):
+        nonlocal out_host
+        env.rewind()
+        out = env.rollout(a_host[i % 2], want_x=False)            # H2D copy of this step's actions inside
+        if out_host is None:
+            out_host = {k: torch.empty(out[k].shape, dtype=out[k].dtype).pin_memory() for k in ("obs", "reward", "done")}
+        for k in out_host:
+            out_host[k].copy_(out[k], non_blocking=True)          # D2H of the step's results
+        return out
+    Ke = max(3, min(K, 10))
+    for i in range(2):
+        one_e2e(i)
+    barrier()
+    t0 = time.perf_counter()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(Ke):
+        one_e2e(i)
+    e1.record()
+    barrier()
+    e2e_ms = sharding.max_over_ranks(e0.elapsed_time(e1), dev)
+    e2e_value = world * env_steps_per_launch * Ke / (e2e_ms * 1e-3)
+    h2d = a_host[0].numel() * 8
+    d2h = sum(v.numel() * v.element_size() for v in out_host.values())
+
+    # ---- Gym-style step mode (one interval per launch), information only
+    env.reset()
+    a_step = torch.zeros(n, 1, dtype=torch.float64, device=dev)
+    for _ in range(5):
+        env.step(a_step)
+    torch.cuda.synchronize()
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s0.record()
+    n_single = 60
+    for _ in range(n_single):
+        env.step(a_step)
+    s1.record()
+    torch.cuda.synchronize()
+    step_ms = s0.elapsed_time(s1) / n_single
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peak, peak_src = hbm_peak()
+    achieved = BYTES_PER_ENV_STEP * env_steps_per_launch / (kern_ms_max * 1e-3) / 1e9
+    line = {
+        "metric": "env-steps/s", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "BASELINE config 3: CSTR, 65 536 envs per GPU x 99 control intervals per launch "
+                               "(N=100, dt=0.25), Gaussian noise 0.1 % (Philox, fp64 Box-Muller), constraints "
+                               "319<=T<=331 with r_penalty, SP reward, normalised obs",
+                   "n_envs_per_gpu": n, "intervals_per_launch": K_STEPS, "integrator": HEADLINE_INTEGRATOR,
+                   "parity": "rtol 1e-6 vs converged oracle at this size: tests/test_gpu_parity.py::test_headline_config_full_size_rtol_1e6",
+                   "l2": "inputs+outputs per launch ~0.48 GB > 126 MB L2; action buffers rotate over a ring of 3",
+                   "parallelism": f"env-sharded x{world}, no collective"},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": None, "peak_source": peak_src, "bytes_per_env_step": BYTES_PER_ENV_STEP,
+                     "kernel_ms": kern_ms_max, "kernel": "pcg::rollout_kernel<Cstr,Tsit5,false>"},
+        "cpu_baseline": cpu,
+        "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "steps": Ke, "ms_per_step": e2e_ms / Ke},
+        "gpu_launches": int(launches),
+        "clocks": clk.summary(),
+        "step_mode": {"env_steps_per_s": n / (step_ms * 1e-3), "ms_per_step": step_ms,
+                      "note": "make_env.step(): one control interval per launch incl. torch-side copies"},
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,159 @@
+// C ABI of libpcgym_b200.so: argument validation + dispatch to the per-model kernel launchers.
+// Declarations and the reference interface each entry point replaces: include/pcgym_b200.h.
+#include <atomic>
+#include <cstring>
+
+#include "launch.cuh"
+
+namespace {
+
+struct ModelInfo {
+  int nx, nu, nd, np;
+  const char* const* names;
+  const double* defaults;
+  pcg::launch_fn launch;
+};
+
+// parameter names / defaults in reference dataclass field order (model_classes.py)
+const char* const kCstrN[] = {"q", "V", "rho", "C", "deltaHr", "EA_over_R", "k0", "UA", "Ti", "Caf"};
+const double kCstrD[] = {100, 100, 1000, 0.239, -5e4, 8750, 7.2e10, 5e4, 350, 1};
+const char* const kFoN[] = {"K", "tau"};
+const double kFoD[] = {1, 0.5};
+const char* const kExN[] = {"Vl", "Vg", "m", "Kla", "eq_exponent", "X0", "Y6"};
+const double kExD[] = {5, 5, 1, 5, 2, 0.6, 0.05};
+const char* const kFtN[] = {"g", "gamma_1", "gamma_2", "k1", "k2", "a1", "a2", "a3", "a4", "A1", "A2", "A3", "A4"};
+const double kFtD[] = {9.81, 0.2, 0.2, 0.00085, 0.00095, 0.0035, 0.0030, 0.0020, 0.0025, 1, 1, 1, 1};
+const char* const kCrN[] = {"ka", "kb", "kc", "kd", "kg", "k1", "k2", "a", "b", "alfa", "ro"};
+const double kCrD[] = {0.923714966, -6754.878558, 0.92229965554, 1.341205945, 48.07514464, -4921.261419,
+                       1.871281405, 0.50523693, 7.271241375, 7.510905767, 2.658};
+const char* const kBfN[] = {"V", "Va", "Kla", "m", "eq_exponent", "O_air", "vm_1", "vm_2", "K1", "K2", "KO_1", "KO_2"};
+const double kBfD[] = {10.0, 15.0, 1.5, 0.5, 1.0, 300, 0.8, 1.0, 0.5, 0.1, 1.5, 0.5};
+
+template <class M>
+constexpr ModelInfo info(const char* const* n, const double* dflt, pcg::launch_fn f) {
+  return ModelInfo{M::NX, M::NU, M::ND, M::NP, n, dflt, f};
+}
+
+const ModelInfo kModels[PCG_MODEL_COUNT] = {
+    info<pcg::Cstr>(kCstrN, kCstrD, pcg::launch_cstr),
+    info<pcg::FirstOrder>(kFoN, kFoD, pcg::launch_first_order),
+    info<pcg::Extraction>(kExN, kExD, pcg::launch_extraction),
+    info<pcg::FourTank>(kFtN, kFtD, pcg::launch_four_tank),
+    info<pcg::Crystallization>(kCrN, kCrD, pcg::launch_crystallization),
+    info<pcg::Biofilm>(kBfN, kBfD, pcg::launch_biofilm),
+};
+
+std::atomic<int64_t> g_launches{0};
+thread_local char t_cuda_err[256] = "";
+
+bool aligned8(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 7u) == 0; }
+
+int validate(const pcg_desc* d, const pcg_io* io, int64_t n_env, int64_t t0, int64_t k_steps) {
+  if (!d || !io) return PCG_E_NULL;
+  if (d->abi_version != PCG_ABI_VERSION || d->struct_bytes != static_cast<int32_t>(sizeof(pcg_desc)))
+    return PCG_E_VERSION;
+  if (d->model < 0 || d->model >= PCG_MODEL_COUNT) return PCG_E_MODEL;
+  if (d->scheme < 0 || d->scheme >= PCG_SCHEME_COUNT) return PCG_E_SCHEME;
+  const bool adaptive = (d->flags & PCG_F_ADAPTIVE) != 0;
+  if (adaptive && d->scheme == PCG_SCHEME_RK4) return PCG_E_SCHEME;
+  const ModelInfo& m = kModels[d->model];
+  if (d->nu_a != m.nu) return PCG_E_DIMS;
+  if (d->nd != 0 && d->nd != m.nd) return PCG_E_DIMS;
+  if (d->nsp < 0 || d->nsp > PCG_MAX_NSP || d->nd_obs < 0 || d->nd_obs > m.nd || d->n_tail < 0 ||
+      d->n_tail > PCG_MAX_NTAIL || d->n_con < 0 || d->n_con > PCG_MAX_NCON)
+    return PCG_E_DIMS;
+  if (d->nd == 0 && d->nd_obs != 0) return PCG_E_DIMS;
+  for (int j = 0; j < d->nsp; ++j)
+    if (d->sp_state[j] < 0 || d->sp_state[j] >= m.nx) return PCG_E_DIMS;
+  for (int j = 0; j < d->nd_obs; ++j)
+    if (d->d_obs[j] < 0 || d->d_obs[j] >= m.nd) return PCG_E_DIMS;
+  if (adaptive ? (d->max_steps < 1 || !(d->rtol > 0.0) || !(d->atol >= 0.0)) : (d->n_sub < 1)) return PCG_E_RANGE;
+  if (!(d->dt > 0.0) || d->N < 2) return PCG_E_RANGE;
+  if (n_env < 1 || n_env > (int64_t{1} << 31) - pcg::kBlock || k_steps < 1 || k_steps > (1 << 24)) return PCG_E_RANGE;
+  if (t0 < 0 || t0 + k_steps > (int64_t{1} << 30)) return PCG_E_RANGE;
+  if (!io->x || !io->a) return PCG_E_NULL;
+  if (d->nsp > 0 && !io->sp) return PCG_E_NULL;
+  if (d->nd > 0) {
+    bool any = false;
+    for (int i = 0; i < m.nd; ++i) any = any || d->d_src[i] >= 0;
+    if (any && !io->dist) return PCG_E_NULL;
+  }
+  if (d->noise == PCG_NOISE_EXTERNAL && !io->z) return PCG_E_NULL;
+  if (d->noise < 0 || d->noise > PCG_NOISE_PHILOX_F32) return PCG_E_RANGE;
+  if (d->n_tail > 0 && !io->tail) return PCG_E_NULL;
+  if ((d->flags & PCG_F_A_DELTA) && (d->flags & PCG_F_NORMALISE_A) && !io->a_save) return PCG_E_NULL;
+  const void* ptrs[] = {io->x, io->a, io->a_save, io->z, io->tail, io->x_traj, io->obs, io->reward, io->g, io->g0,
+                        io->h_carry};
+  for (const void* p : ptrs)
+    if (p && !aligned8(p)) return PCG_E_ALIGN;
+  return PCG_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int pcg_abi_version(void) { return PCG_ABI_VERSION; }
+int pcg_sizeof_desc(void) { return static_cast<int>(sizeof(pcg_desc)); }
+int pcg_sizeof_io(void) { return static_cast<int>(sizeof(pcg_io)); }
+
+int pcg_model_dims(int model, int* nx, int* nu, int* nd, int* nparam) {
+  if (model < 0 || model >= PCG_MODEL_COUNT) return PCG_E_MODEL;
+  const ModelInfo& m = kModels[model];
+  if (nx) *nx = m.nx;
+  if (nu) *nu = m.nu;
+  if (nd) *nd = m.nd;
+  if (nparam) *nparam = m.np;
+  return PCG_OK;
+}
+
+const char* pcg_model_param_name(int model, int i) {
+  if (model < 0 || model >= PCG_MODEL_COUNT || i < 0 || i >= kModels[model].np) return nullptr;
+  return kModels[model].names[i];
+}
+
+int pcg_model_param_default(int model, int i, double* value) {
+  if (model < 0 || model >= PCG_MODEL_COUNT) return PCG_E_MODEL;
+  if (i < 0 || i >= kModels[model].np) return PCG_E_RANGE;
+  if (!value) return PCG_E_NULL;
+  *value = kModels[model].defaults[i];
+  return PCG_OK;
+}
+
+int pcg_rollout(const pcg_desc* d, const pcg_io* io, int64_t n_env, int64_t t0, int64_t k_steps, void* cuda_stream) {
+  const int rc = validate(d, io, n_env, t0, k_steps);
+  if (rc != PCG_OK) return rc;
+  const cudaError_t e = kModels[d->model].launch(*d, *io, n_env, static_cast<int>(t0), static_cast<int>(k_steps),
+                                                 static_cast<cudaStream_t>(cuda_stream));
+  if (e != cudaSuccess) {
+    std::strncpy(t_cuda_err, cudaGetErrorString(e), sizeof(t_cuda_err) - 1);
+    return PCG_E_CUDA;
+  }
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return PCG_OK;
+}
+
+int pcg_step(const pcg_desc* d, const pcg_io* io, int64_t n_env, int64_t t, void* cuda_stream) {
+  return pcg_rollout(d, io, n_env, t, 1, cuda_stream);
+}
+
+int64_t pcg_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+const char* pcg_strerror(int status) {
+  switch (status) {
+    case PCG_OK: return "ok";
+    case PCG_E_NULL: return "required pointer is NULL";
+    case PCG_E_VERSION: return "pcg_desc ABI version / size mismatch";
+    case PCG_E_MODEL: return "unknown model id";
+    case PCG_E_SCHEME: return "unknown integrator scheme (or adaptive RK4)";
+    case PCG_E_DIMS: return "descriptor dimensions inconsistent with the model";
+    case PCG_E_RANGE: return "n_env / k_steps / t / integrator option out of range";
+    case PCG_E_ALIGN: return "fp64 device pointer not 8-byte aligned";
+    case PCG_E_CUDA: return "CUDA runtime error";
+  }
+  return "unknown status";
+}
+
+const char* pcg_last_cuda_error(void) { return t_cuda_err; }
+
+}  // extern "C"

@@ -1,0 +1,199 @@
+// Device right-hand sides of the registry models (reference src/pcgym/model_classes.py).
+//
+// Every model is a struct with compile-time dimensions
+//   NX   states                       NU  manipulated inputs
+//   ND   disturbance input channels   NP  parameters theta (reference dataclass field order)
+// a derived-constant block `P` built once per thread from theta, and
+//   rhs(P, x[NX], uk[NU+ND], dx[NX])
+// where uk = [manipulated inputs | disturbance channels].  The reference switches on
+// `u.size` to decide whether the disturbance channels override parameters
+// (model_classes.py:48-51, 382-385); here the caller always fills uk[NU..NU+ND) -- with the
+// supplied disturbance or with the parameter default -- so the RHS has no branch.
+//
+// Arithmetic is fp64 throughout.  Expressions are regrouped for fewer DFMA/MUFU
+// operations (constants folded, reciprocals hoisted); parity is defined against the
+// converged solution of the reference RHS to rtol 1e-6, and the regrouping perturbs
+// results at the 1e-15 level.
+#pragma once
+#include <cstdint>
+
+namespace pcg {
+
+#define PCG_DEV __device__ __forceinline__
+
+// ---------------------------------------------------------------------------------------
+// cstr -- model_classes.py:23-62
+// theta: q V rho C deltaHr EA_over_R k0 UA Ti Caf       disturbances: Ti, Caf
+struct Cstr {
+  static constexpr int NX = 2, NU = 1, ND = 2, NP = 10;
+  struct P { double thru, k0, neg_ear, c_heat, c_cool; };
+  PCG_DEV static P make(const double* th) {
+    P p;
+    p.thru = th[0] / th[1];                       // q / V
+    p.k0 = th[6];
+    p.neg_ear = -th[5];                           // -EA/R
+    p.c_heat = (-th[4]) / (th[2] * th[3]);        // (-deltaHr) / (rho C)
+    p.c_cool = th[7] / (th[2] * th[3] * th[1]);   // UA / (rho C V)
+    return p;
+  }
+  static constexpr int d_param[ND] = {8, 9};      // theta index of each disturbance default
+  PCG_DEV static void rhs(const P& p, const double* x, const double* u, double* dx) {
+    const double ca = x[0], T = x[1];
+    const double Tc = u[0], Ti = u[1], Caf = u[2];
+    const double rate = p.k0 * exp(p.neg_ear / T) * ca;          // :52
+    dx[0] = fma(p.thru, Caf - ca, -rate);                        // :53
+    dx[1] = fma(p.thru, Ti - T, fma(p.c_heat, rate, p.c_cool * (Tc - T)));   // :54-58
+  }
+};
+
+// ---------------------------------------------------------------------------------------
+// first_order_system -- model_classes.py:296-343      theta: K tau
+struct FirstOrder {
+  static constexpr int NX = 1, NU = 1, ND = 0, NP = 2;
+  struct P { double K, inv_tau; };
+  PCG_DEV static P make(const double* th) { return P{th[0], 1.0 / th[1]}; }
+  static constexpr int d_param[1] = {0};
+  PCG_DEV static void rhs(const P& p, const double* x, const double* u, double* dx) {
+    dx[0] = fma(p.K, u[0], -x[0]) * p.inv_tau;                   // :322
+  }
+};
+
+// ---------------------------------------------------------------------------------------
+// multistage_extraction -- model_classes.py:346-430
+// theta: Vl Vg m Kla eq_exponent X0 Y6                 disturbances: X0, Y6
+// states interleaved X1 Y1 ... X5 Y5
+struct Extraction {
+  static constexpr int NSTAGE = 5;
+  static constexpr int NX = 2 * NSTAGE, NU = 2, ND = 2, NP = 7;
+  struct P { double inv_vl, inv_vg, inv_m, kla_vl, expo; bool square; };
+  PCG_DEV static P make(const double* th) {
+    P p;
+    p.inv_vl = 1.0 / th[0];
+    p.inv_vg = 1.0 / th[1];
+    p.inv_m = 1.0 / th[2];
+    p.kla_vl = th[3] * th[0];
+    p.expo = th[4];
+    p.square = (th[4] == 2.0);
+    return p;
+  }
+  static constexpr int d_param[ND] = {5, 6};
+  PCG_DEV static void rhs(const P& p, const double* x, const double* u, double* dx) {
+    const double L = u[0], G = u[1], X0 = u[2], Y6 = u[3];
+#pragma unroll
+    for (int i = 0; i < NSTAGE; ++i) {
+      const double X = x[2 * i], Y = x[2 * i + 1];
+      const double ye = p.square ? Y * Y : pow(Y, p.expo);       // :387-391
+      const double Q = p.kla_vl * fma(-ye, p.inv_m, X);          // :393-397
+      const double xin = (i == 0) ? X0 : x[2 * i - 2];
+      const double yin = (i == NSTAGE - 1) ? Y6 : x[2 * i + 3];
+      dx[2 * i] = p.inv_vl * fma(L, xin - X, -Q);                // :399-410
+      dx[2 * i + 1] = p.inv_vg * fma(G, yin - Y, Q);
+    }
+  }
+};
+
+// ---------------------------------------------------------------------------------------
+// four_tank -- model_classes.py:864-931
+// theta: g gamma_1 gamma_2 k1 k2 a1 a2 a3 a4 A1 A2 A3 A4   (disturbances ["None"]: inert)
+struct FourTank {
+  static constexpr int NX = 4, NU = 2, ND = 0, NP = 13;
+  struct P { double g2, o11, o13, o22, o24, o33, o44, p11, p22, p32, p41; };
+  PCG_DEV static P make(const double* th) {
+    P p;
+    p.g2 = 2.0 * th[0];
+    const double A1 = th[9], A2 = th[10], A3 = th[11], A4 = th[12];
+    p.o11 = -th[5] / A1;  p.o13 = th[7] / A1;
+    p.o22 = -th[6] / A2;  p.o24 = th[8] / A2;
+    p.o33 = -th[7] / A3;  p.o44 = -th[8] / A4;
+    p.p11 = (th[1] * th[3]) / A1;
+    p.p22 = (th[2] * th[4]) / A2;
+    p.p32 = ((1.0 - th[2]) * th[4]) / A3;
+    p.p41 = ((1.0 - th[1]) * th[3]) / A4;
+    return p;
+  }
+  static constexpr int d_param[1] = {0};
+  PCG_DEV static void rhs(const P& p, const double* x, const double* u, double* dx) {
+    const double s1 = sqrt(p.g2 * x[0]), s2 = sqrt(p.g2 * x[1]);   // NaN for h < 0, as the reference
+    const double s3 = sqrt(p.g2 * x[2]), s4 = sqrt(p.g2 * x[3]);
+    dx[0] = fma(p.o11, s1, fma(p.o13, s3, p.p11 * u[0]));          // :906
+    dx[1] = fma(p.o22, s2, fma(p.o24, s4, p.p22 * u[1]));          // :907
+    dx[2] = fma(p.o33, s3, p.p32 * u[1]);                          // :908
+    dx[3] = fma(p.o44, s4, p.p41 * u[0]);                          // :909
+  }
+};
+
+// ---------------------------------------------------------------------------------------
+// crystallization -- model_classes.py:1232-1345
+// theta: ka kb kc kd kg k1 k2 a b alfa ro      disturbances ka, kg, UA are declared (:1342)
+// but the RHS reads only u[0] (:1299), so they are carried in uk and ignored.
+struct Crystallization {
+  static constexpr int NX = 7, NU = 1, ND = 3, NP = 11;
+  struct P { double ka, kb, kc, kd, kg, k1, k2, a, b, half_ro_alfa; };
+  PCG_DEV static P make(const double* th) {
+    return P{th[0], th[1], th[2], th[3], th[4], th[5], th[6], th[7], th[8], 0.5 * th[10] * th[9]};
+  }
+  static constexpr int d_param[ND] = {0, 4, -1};   // "UA" is not a parameter of this model
+  PCG_DEV static void rhs(const P& p, const double* x, const double* u, double* dx) {
+    const double mu0 = x[0], mu1 = x[1], mu2 = x[2], mu3 = x[3], conc = x[4];
+    const double TK = u[0] + 273.15;
+    const double Ceq = fma(TK, fma(-0.00292874, TK, 3.579165), -686.2686);      // :1302
+    const double S = fma(conc, 1e3, -Ceq);                                      // :1303
+    const double inv_TK = 1.0 / TK;
+    const double lnS = log(fabs(S));            // (S^2)^(k/2) = |S|^k = exp(k ln|S|)
+    const double lnM = log(fabs(mu3));
+    const double B0 = p.ka * exp(fma(p.kb, inv_TK, fma(p.kc, lnS, p.kd * lnM)));   // :1304
+    const double G = p.kg * exp(fma(p.k1, inv_TK, p.k2 * lnS));                    // :1305
+    const double d0 = B0;
+    const double d1 = G * fma(p.a, mu0, p.b * mu1 * 1e-4) * 1e4;                   // :1308
+    const double d2 = 2.0 * G * fma(p.a * mu1, 1e-4, p.b * mu2 * 1e-8) * 1e8;      // :1309
+    const double m23 = fma(p.a * mu2, 1e-8, p.b * mu3 * 1e-12);
+    const double d3 = 3.0 * G * m23 * 1e12;                                        // :1310
+    const double dc = -p.half_ro_alfa * G * m23;                                   // :1311
+    const double mu1sq = mu1 * mu1;
+    const double CV = sqrt(mu2 * mu0 / mu1sq - 1.0);                               // :1313
+    const double num = fma(fma(d2, mu0, mu2 * d0), mu1sq, -(mu2 * mu0 * 2.0 * mu1 * d1));
+    const double dCV = (1.0 / fma(2.0, CV, 1e-10)) * num / fma(mu1sq, mu1sq, 1e-10);   // :1314
+    const double dLn = fma(d1, mu0, -(mu1 * d0)) / fma(mu0, mu0, 1e-10);           // :1315
+    dx[0] = d0; dx[1] = d1; dx[2] = d2; dx[3] = d3; dx[4] = dc; dx[5] = dCV; dx[6] = dLn;
+  }
+};
+
+// ---------------------------------------------------------------------------------------
+// biofilm_reactor -- model_classes.py:1046-1155
+// theta: V Va Kla m eq_exponent O_air vm_1 vm_2 K1 K2 KO_1 KO_2    inputs F Fr S1_F S2_F S3_F
+struct Biofilm {
+  static constexpr int NX = 16, NU = 5, ND = 0, NP = 12;
+  struct P { double inv_v, inv_va, kla, o_eq, vm1, vm2, K1, K2, KO1, KO2; };
+  PCG_DEV static P make(const double* th) {
+    P p;
+    p.inv_v = 1.0 / th[0];
+    p.inv_va = 1.0 / th[1];
+    p.kla = th[2];
+    p.o_eq = ((th[4] == 1.0) ? th[5] : pow(th[5], th[4])) / th[3];   // O_air^e / m  (:1112)
+    p.vm1 = th[6]; p.vm2 = th[7]; p.K1 = th[8]; p.K2 = th[9]; p.KO1 = th[10]; p.KO2 = th[11];
+    return p;
+  }
+  static constexpr int d_param[1] = {0};
+  PCG_DEV static void rhs(const P& p, const double* x, const double* u, double* dx) {
+    const double F = u[0], Fr = u[1];
+    const double frv = Fr * p.inv_v, fra = Fr * p.inv_va, fa = F * p.inv_va;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const double S1 = x[4 * k], S2 = x[4 * k + 1], S3 = x[4 * k + 2], O = x[4 * k + 3];
+      const int up = (k == 0) ? 12 : 4 * (k - 1);                  // absorber feeds stage 1
+      // Monod terms (:1091-1100); one divide per reaction
+      const double r1 = (p.vm1 * S1 * O) / ((p.K1 + S1) * (p.KO1 + O));
+      const double r2 = (p.vm2 * S2 * O) / ((p.K2 + S2) * (p.KO2 + O));
+      dx[4 * k] = fma(frv, x[up] - S1, r1);                        // - rs1, rs1 = -r1
+      dx[4 * k + 1] = fma(frv, x[up + 1] - S2, r2 - r1);           // - rs2, rs2 = r1 - r2
+      dx[4 * k + 2] = fma(frv, x[up + 2] - S3, -r2);               // - rs3, rs3 = r2
+      dx[4 * k + 3] = fma(frv, x[up + 3] - O, fma(3.5, r1, 1.1 * r2));   // - ro, ro = -3.5 r1 - 1.1 r2
+    }
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+      dx[12 + j] = fma(fra, x[8 + j] - x[12 + j], fa * (u[2 + j] - x[12 + j]));   // :1127-1129
+    dx[15] = fma(fra, x[11] - x[15], p.kla * (p.o_eq - x[15]));                   // :1130
+  }
+};
+
+}  // namespace pcg

@@ -1,0 +1,656 @@
+"""`make_env`: the reference's Gymnasium surface (src/pcgym/pcgym.py:31-500) over the B200 kernels.
+
+Drop-in contract
+  * same constructor argument (`env_params` dict, same 31 keys), same attributes
+    (N, tsim, dt, Nx, Nx_oracle, Nu, Nd, Nd_model, SP, x0, t, state, obs, done, info, model, a_save, ...),
+    same `reset(seed=0) -> (obs, info)` and `step(a) -> (obs, r, done, False, info)`;
+  * `n_envs` (default 1) independent copies advance per launch.  With `n_envs == 1` and numpy input
+    the return types are the reference's (float64 ndarray / float / bool); otherwise torch CUDA
+    tensors: obs [n_envs, Nx], reward [n_envs], done [n_envs] bool, truncated [n_envs] bool;
+  * `rollout(actions)` advances K control intervals in ONE launch (state stays in registers).
+
+Everything numeric on the step path happens inside `libpcgym_b200.so` (pcg_step / pcg_rollout); this
+file parses the configuration into a `pcg_desc`, owns the device tensors (struct-of-arrays
+[field][env], fp64) and mirrors the reference's bookkeeping.  There is no CPU fallback.
+
+New optional keys: `n_envs`, `device`, `seed`, `env_id0`, `noise_mode` ("philox" | "philox_f32" |
+"external"), `integrator` = {"scheme": "tsit5"|"dopri5"|"rk4", "adaptive": bool, "rtol", "atol",
+"n_sub", "max_steps"}, `constraint_units` ("reference" | "physical"), per-env `x0` [n_envs, Nx],
+per-env `SP[k]` / `disturbances[k]` [n_envs, N].
+"""
+from __future__ import annotations
+
+import copy
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _native as nat
+from . import models as _models
+from .spaces import Box
+
+_DEFAULT_INTEGRATOR = {"scheme": "tsit5", "adaptive": True, "rtol": 1e-8, "atol": 1e-8, "n_sub": 1,
+                       "max_steps": 4096}     # mirrors the reference's jax path: Tsit5 + PID(1e-8, 1e-8), integrator.py:57-61
+
+
+def _np(a):
+    if isinstance(a, torch.Tensor):
+        return a.detach().cpu().numpy().astype(np.float64)
+    return np.asarray(a, dtype=np.float64)
+
+
+class make_env:
+    metadata = {"render_modes": []}
+
+    # ------------------------------------------------------------------ construction (host only)
+    def __init__(self, env_params: dict) -> None:
+        if not isinstance(env_params, dict):
+            raise ValueError("env_params must be a dictionary")                    # pcgym.py:40-41
+        nat.lib()                                                                  # fail loudly if the .so is absent
+        P = self.env_params = copy.deepcopy(env_params)
+        self.n_envs = int(P.get("n_envs", 1))
+        if self.n_envs < 1:
+            raise ValueError("n_envs must be >= 1")
+        self.device = torch.device(P.get("device", "cuda"))
+        self.seed = int(P.get("seed", 0))
+        self.env_id0 = int(P.get("env_id0", 0))
+        self._copy_outputs = bool(P.get("copy_outputs", True))
+
+        # pcgym.py:56-61
+        self.a_delta = P.get("a_delta", False)
+        if self.a_delta:
+            self.a_0 = P["a_0"]
+        self.normalise_a = P.get("normalise_a", True)
+        self.normalise_o = P.get("normalise_o", True)
+
+        # pcgym.py:68-92
+        self._a_lo, self._a_hi = _np(P["a_space"]["low"]).ravel(), _np(P["a_space"]["high"]).ravel()
+        n_a = self._a_lo.shape[0]
+        self.action_space = Box(-np.ones(n_a), np.ones(n_a)) if self.normalise_a else Box(self._a_lo, self._a_hi)
+        o_lo, o_hi = _np(P["o_space"]["low"]).ravel(), _np(P["o_space"]["high"]).ravel()
+
+        # pcgym.py:94-111
+        self.maximise_reward = True
+        self.SP = P.get("SP")
+        self.custom_reward = P.get("custom_reward") is not None
+        if self.custom_reward:
+            self.custom_reward_f = P["custom_reward"]
+            self.reward = None
+        elif self.SP is not None:
+            self.reward = "SP_reward_fn"
+        else:
+            self.reward = "batch_reward_fn"
+            self.reward_states = P["reward_states"]
+            self.maximise_reward = P["maximise_reward"]
+        self.N = int(P["N"])
+        self.tsim = P["tsim"]
+        self.x0 = P["x0"]
+        self.integration_method = P.get("integration_method", "b200")
+        if self.integration_method not in ("b200", "casadi", "jax"):              # integrator.py:33-36
+            raise AssertionError("integration_method must be 'b200' (or the reference's 'casadi' / 'jax', which map to it)")
+        self.dt = self.tsim / self.N
+        self.done = False
+        integ = dict(_DEFAULT_INTEGRATOR)
+        integ.update(P.get("integrator", {}))
+        if integ["scheme"] not in nat.SCHEMES:
+            raise ValueError(f"unknown integrator scheme {integ['scheme']!r}")
+        if integ["scheme"] == "rk4":
+            integ["adaptive"] = False
+        self.integrator = integ
+
+        # pcgym.py:127-158
+        if P.get("custom_model") is not None:
+            raise NotImplementedError(
+                "custom_model is a Python callable and cannot run inside the CUDA kernel; "
+                "only registry models are supported by the B200 engine")
+        self.model = _models.get(P.get("model"), self.integration_method)
+        minfo = self.model.info()
+
+        # pcgym.py:160-165
+        self.Nx_oracle = len(minfo["states"])
+        self.Nx = self.Nx_oracle + (len(self.SP) if self.SP is not None else 0)
+        self.Nu = len(minfo["inputs"])
+        if n_a != self.Nu:
+            raise ValueError(f"a_space has {n_a} entries but model '{self.model.name}' has {self.Nu} inputs")
+
+        # pcgym.py:167-199
+        self.disturbance_active = False
+        self.Nd = self.Nd_model = 0
+        if P.get("disturbances") is not None:
+            self.disturbance_active = True
+            self.disturbances = P["disturbances"]
+            self.Nd = len(self.disturbances)
+            self.Nd_model = len(minfo["disturbances"])
+            for k in minfo["disturbances"]:
+                if k not in self.disturbances and str(k) not in minfo["parameters"]:
+                    raise KeyError(str(k))                                         # pcgym.py:400 on the reference
+            unknown = [k for k in self.disturbances if k not in minfo["disturbances"]]
+            if unknown:
+                raise KeyError(f"disturbances {unknown} are not channels of model '{self.model.name}' "
+                               f"({minfo['disturbances']})")
+            self.Nu += self.Nd_model
+            self.Nx += self.Nd
+            o_lo = np.concatenate((o_lo, _np(P["disturbance_bounds"]["low"]).ravel()))
+            o_hi = np.concatenate((o_hi, _np(P["disturbance_bounds"]["high"]).ravel()))
+
+        # pcgym.py:212-252 (observation-only in the reference: sampled values never reach the dynamics)
+        self.uncertainty = False
+        self.NUn = 0
+        self.uncertainty_percentages = None
+        self.empirical_distribution = None
+        if P.get("uncertainty_percentages") is not None or P.get("empirical_distribution") is not None:
+            self.uncertainty = True
+            if P.get("uncertainty_percentages") is not None:
+                self.uncertainty_percentages = P["uncertainty_percentages"]
+                names = [k for k in self.uncertainty_percentages if k != "x0"]
+                self.distribution = P.get("distribution")
+            else:
+                self.empirical_distribution = P["empirical_distribution"]
+                names = [k for k in self.empirical_distribution if k != "x0"]
+            self.original_param_values = {k: getattr(self.model, k) for k in names}
+            self._unc_names = names
+            self.NUn = len(names)
+            o_lo = np.concatenate((o_lo, _np(P["uncertainty_bounds"]["low"]).ravel()))
+            o_hi = np.concatenate((o_hi, _np(P["uncertainty_bounds"]["high"]).ravel()))
+        self.observation_space_base = Box(o_lo, o_hi)
+        n_o = o_lo.shape[0]
+        self.observation_space = Box(-np.ones(n_o), np.ones(n_o)) if self.normalise_o else self.observation_space_base
+        self._n_obs = self.Nx + self.NUn
+        if n_o != self._n_obs:
+            raise ValueError(f"o_space (+ disturbance/uncertainty bounds) has {n_o} entries, state vector has {self._n_obs}")
+
+        # pcgym.py:63-66, 208-211
+        self.noise_percentage = P.get("noise_percentage")
+        if self.noise_percentage is not None:
+            self.noise_percentage_float = isinstance(self.noise_percentage, float)
+        self.partial_observation = P.get("partial_observation") or False
+        self.noise_mode = P.get("noise_mode", "philox")
+        if self.noise_mode not in ("philox", "philox_f32", "external"):
+            raise ValueError("noise_mode must be 'philox', 'philox_f32' or 'external'")
+
+        # pcgym.py:113-125 (after the model so the affine probe knows the dimensions)
+        self.constraint_active = False
+        self.r_penalty = False
+        self.info = {}
+        self.n_con = 0
+        if P.get("constraints") is not None:
+            self.constraints = P["constraints"]
+            self.done_on_constraint = P["done_on_cons_vio"]
+            self.r_penalty = P["r_penalty"]
+            self.constraint_active = True
+            self._G, self._h = self._affine_constraints()
+            self.n_con = self._h.shape[0]
+            if self.n_con > nat.MAX_NCON:
+                raise ValueError(f"at most {nat.MAX_NCON} constraints are supported")
+
+        self._host_tables()
+        self._desc = self._build_desc()
+        self._dev_ready = False
+        self.t = 0
+
+    # ------------------------------------------------------------------ constraints: callable -> affine form
+    def _affine_constraints(self):
+        """The reference takes a Python callable g(x, u) <= 0 (pcgym.py:571-572).  A callable cannot run
+        in the kernel, so it is probed: g(0), g(e_i) give h and the columns of G, and random points verify
+        that g really is affine in (state, uk).  Every constraint in the reference's docs and tests is."""
+        nx, nu = self._n_obs, self.Nu
+        g = lambda s, u: np.asarray(self.constraints(s, u), dtype=np.float64).reshape(-1)
+        h = g(np.zeros(nx), np.zeros(nu))
+        G = np.zeros((h.shape[0], nx + nu))
+        for i in range(nx + nu):
+            e = np.zeros(nx + nu)
+            e[i] = 1.0
+            G[:, i] = g(e[:nx], e[nx:]) - h
+        rng = np.random.default_rng(0)
+        s0 = np.ones(nx)                                   # representative magnitudes for the affinity check
+        x0 = np.abs(_np(self.x0).reshape(-1, _np(self.x0).shape[-1])[0])
+        s0[: min(nx, x0.shape[0])] = x0[:nx]
+        u0 = np.ones(nu)
+        u0[: self._a_hi.shape[0]] = np.maximum(np.abs(self._a_hi), np.abs(self._a_lo))
+        scale = np.concatenate((np.where(s0 > 0, s0, 1.0), np.where(u0 > 0, u0, 1.0)))
+        for _ in range(4):
+            v = rng.normal(size=nx + nu) * scale
+            want, got = g(v[:nx], v[nx:]), G @ v + h
+            if not np.allclose(want, got, rtol=1e-9, atol=1e-9 * (1 + np.abs(want).max())):
+                raise NotImplementedError(
+                    "constraints(x, u) is not affine in (x, u): only affine constraints can be fused "
+                    "into the B200 step kernel")
+        return G, h
+
+    # ------------------------------------------------------------------ host tables (setpoints, disturbances, x0)
+    def _per_time(self, v, what):
+        """-> (array [N] shared) or (array [n_envs, N] per env)."""
+        a = _np(v)
+        if a.ndim == 1:
+            if a.shape[0] < self.N:
+                raise IndexError(f"{what} has {a.shape[0]} entries, needs N = {self.N}")
+            return a[: self.N], False
+        if a.shape != (self.n_envs, a.shape[1]) or a.shape[1] < self.N:
+            raise ValueError(f"{what} must be [N] or [n_envs, N]")
+        return a[:, : self.N], True
+
+    def _host_tables(self):
+        names = self.model.info()["states"]
+        # setpoints, dict order (pcgym.py:432-438)
+        self._sp_keys = list(self.SP.keys()) if self.SP is not None else []
+        if len(self._sp_keys) > nat.MAX_NSP:
+            raise ValueError(f"at most {nat.MAX_NSP} setpoints are supported")
+        for k in self._sp_keys:
+            if k not in names:
+                raise ValueError(f"'{k}' is not in list")                          # names.index(k), pcgym.py:553
+        sp = [self._per_time(self.SP[k], f"SP['{k}']") for k in self._sp_keys]
+        self._sp_per_env = any(pe for _, pe in sp)
+        if self._sp_keys:
+            if self._sp_per_env:     # [N, nsp, n_envs]
+                self._sp_host = np.stack([np.broadcast_to(a if pe else a[None], (self.n_envs, self.N)).T
+                                          for a, pe in sp], axis=1)
+            else:                    # [nsp, N]
+                self._sp_host = np.stack([a for a, _ in sp])
+        else:
+            self._sp_host = None
+        # disturbances in model order (pcgym.py:392-405)
+        self._d_keys = [k for k in self.model.info()["disturbances"] if self.disturbance_active and k in self.disturbances]
+        ds = [self._per_time(self.disturbances[k], f"disturbances['{k}']") for k in self._d_keys]
+        self._d_per_env = any(pe for _, pe in ds)
+        if self._d_keys:
+            if self._d_per_env:
+                self._d_host = np.stack([np.broadcast_to(a if pe else a[None], (self.n_envs, self.N)).T
+                                         for a, pe in ds], axis=1)
+            else:
+                self._d_host = np.stack([a for a, _ in ds])
+        else:
+            self._d_host = None
+        # x0: [Nx_full] or [n_envs, Nx_full]; only the first Nx_oracle + nSP entries are used (pcgym.py:284)
+        x0 = _np(self.x0)
+        if x0.ndim == 1:
+            x0 = np.broadcast_to(x0, (self.n_envs, x0.shape[0]))
+        elif x0.shape[0] != self.n_envs:
+            raise ValueError("per-env x0 must be [n_envs, Nx]")
+        need = self.Nx_oracle + len(self._sp_keys)
+        if x0.shape[1] != need:
+            raise ValueError(f"x0 has {x0.shape[1]} entries; expected {need} (model states + setpoints)")
+        self._x0_host = np.ascontiguousarray(x0.T)        # [Nx_oracle + nsp, n_envs]
+
+    # ------------------------------------------------------------------ descriptor
+    def _build_desc(self) -> nat.Desc:
+        d = nat.Desc()
+        P = self.env_params
+        nx = self.Nx_oracle
+        names = self.model.info()["states"]
+        d.abi_version, d.struct_bytes = nat.ABI_VERSION, ctypes.sizeof(nat.Desc)
+        d.model = self.model.model_id
+        d.scheme = nat.SCHEMES[self.integrator["scheme"]]
+        flags = 0
+        flags |= nat.F_NORMALISE_A if self.normalise_a is True else 0
+        flags |= nat.F_NORMALISE_O if self.normalise_o is True else 0
+        flags |= nat.F_A_DELTA if (self.a_delta and self.normalise_a) else 0
+        flags |= nat.F_R_PENALTY if self.r_penalty else 0
+        flags |= nat.F_DONE_ON_VIOLATION if (self.constraint_active and self.done_on_constraint) else 0
+        flags |= nat.F_ADAPTIVE if self.integrator["adaptive"] else 0
+        d.flags = flags
+        d.n_sub, d.max_steps = int(self.integrator["n_sub"]), int(self.integrator["max_steps"])
+        d.rtol, d.atol = float(self.integrator["rtol"]), float(self.integrator["atol"])
+        d.N, d.dt = self.N, float(self.dt)
+        theta = self.model.theta()
+        for i, v in enumerate(theta):
+            d.theta[i] = v
+
+        nu_a = self._a_lo.shape[0]
+        d.nu_a = nu_a
+        params = self.model.info()["parameters"]
+        model_d = [] if self.model.disturbances in (["None"], []) else self.model.disturbances
+        d.nd = len(model_d) if self.disturbance_active else 0
+        for i in range(nat.MAX_ND):
+            d.d_src[i] = -1
+        for i, k in enumerate(model_d):
+            d.d_default[i] = float(params.get(k, 0.0))
+            if self.disturbance_active and k in self._d_keys:
+                d.d_src[i] = self._d_keys.index(k)
+        for j in range(nu_a):
+            half = (self._a_hi[j] - self._a_lo[j]) / 2.0
+            d.a_scale[j], d.a_off[j] = half, self._a_lo[j] + half
+            if self.a_delta:
+                d.a_act_lo[j] = float(_np(P["a_space_act"]["low"]).ravel()[j])
+                d.a_act_hi[j] = float(_np(P["a_space_act"]["high"]).ravel()[j])
+
+        d.nsp = len(self._sp_keys)
+        r_scale = P.get("r_scale", {})
+        for j, k in enumerate(self._sp_keys):
+            d.sp_state[j] = names.index(k)
+            d.r_scale[j] = float(r_scale.get(k, 1))
+            d.sp_init[j] = float(self._x0_host[nx + j, 0])
+        d.nd_obs = len(self._d_keys)
+        for j, k in enumerate(self._d_keys):
+            d.d_obs[j] = model_d.index(k)
+        d.n_tail = self.NUn
+        lo, hi = self.observation_space_base.low.astype(np.float64), self.observation_space_base.high.astype(np.float64)
+        for i in range(self._n_obs):
+            span = hi[i] - lo[i]
+            d.o_scale[i] = 2.0 / span if span != 0 else float("inf")
+            d.o_off[i] = -2.0 * lo[i] / span - 1.0 if span != 0 else float("nan")
+        mask = 0
+        if self.partial_observation:
+            for i in range(nx):
+                if names[i] not in self.partial_observation:
+                    mask |= 1 << i
+        d.obs_zero_mask = mask
+
+        d.noise = nat.NOISE["off"]
+        if P.get("noise", False):
+            if self.noise_percentage is None:
+                raise AttributeError("noise=True needs noise_percentage")          # pcgym.py:455 on the reference
+            d.noise = nat.NOISE[self.noise_mode]
+            for i in range(nx):
+                if self.noise_percentage_float:
+                    d.noise_pct[i] = float(self.noise_percentage)
+                elif names[i] in self.noise_percentage:
+                    d.noise_pct[i] = float(self.noise_percentage[str(names[i])])
+        d.seed, d.env_id0 = self.seed & (2 ** 64 - 1), self.env_id0
+
+        d.penalty = 1000.0
+        if self.custom_reward:
+            d.reward = nat.REWARD["none"]
+        elif self.reward == "SP_reward_fn":
+            d.reward = nat.REWARD["sp"]
+        else:
+            d.reward = nat.REWARD["batch"]
+            for s in self.reward_states:                                            # pcgym.py:519-527
+                if str(s) in names:
+                    w = float(r_scale.get(s, 1))
+                    d.batch_w[names.index(s)] += w if self.maximise_reward else -w
+
+        d.n_con = self.n_con
+        if self.constraint_active:
+            G, h = self._G.copy(), self._h.copy()
+            n_s = self._n_obs
+            if P.get("constraint_units", "reference") == "reference":
+                # constraint_check un-normalises values that are already physical (pcgym.py:597-608);
+                # both maps are affine, so the quirk folds into G and h.
+                if self.normalise_a is True:
+                    if nu_a not in (1, self.Nu):
+                        raise ValueError(f"operands could not be broadcast together with shapes ({self.Nu},) ({nu_a},)")
+                    sa = np.broadcast_to((self._a_hi - self._a_lo) / 2.0, (self.Nu,))
+                    la = np.broadcast_to(self._a_lo, (self.Nu,))
+                    h = h + G[:, n_s:] @ (sa + la)
+                    G[:, n_s:] = G[:, n_s:] * sa
+                if self.normalise_o is True:
+                    so = (hi - lo) / 2.0
+                    h = h + G[:, :n_s] @ (so + lo)
+                    G[:, :n_s] = G[:, :n_s] * so
+            for c in range(self.n_con):
+                mx = mu = 0
+                for i in range(n_s):
+                    d.con_gx[c][i] = G[c, i]
+                    if G[c, i] != 0.0:
+                        mx |= 1 << i
+                for i in range(self.Nu):
+                    # uk on the device always carries the model's disturbance channels after the actions
+                    d.con_gu[c][i] = G[c, n_s + i]
+                    if G[c, n_s + i] != 0.0:
+                        mu |= 1 << i
+                d.con_h[c] = h[c]
+                d.con_mask_x[c], d.con_mask_u[c] = mx, mu
+        return d
+
+    # ------------------------------------------------------------------ device state
+    def _ensure_device(self):
+        if self._dev_ready:
+            return
+        if self.device.type != "cuda" or not torch.cuda.is_available():
+            raise RuntimeError("pcgym_b200 needs a CUDA device (no CPU fallback); "
+                               f"device={self.device}, cuda available={torch.cuda.is_available()}")
+        dev, n, f64 = self.device, self.n_envs, torch.float64
+        nx = self.Nx_oracle
+        z = lambda *s, dtype=f64: torch.zeros(*s, dtype=dtype, device=dev)
+        self._x = z(nx, n)
+        self._x0_dev = torch.from_numpy(self._x0_host).to(dev)
+        self._sp_dev = torch.from_numpy(np.ascontiguousarray(self._sp_host)).to(dev) if self._sp_host is not None else None
+        self._d_dev = torch.from_numpy(np.ascontiguousarray(self._d_host)).to(dev) if self._d_host is not None else None
+        self._a_save = z(self._a_lo.shape[0], n) if self.a_delta else None
+        self._tail = z(max(self.NUn, 1), n) if self.NUn else None
+        self._done_state = z(n, dtype=torch.uint8)
+        self._status = z(n, dtype=torch.uint8)
+        self._h_carry = z(n)
+        self._n_rhs = z(n, dtype=torch.int32)
+        # cons_info lives as [N, n_con, n_envs] so the kernel writes rows in place; exposed as (n_con, N, n_envs)
+        self._cons = z(self.N, max(self.n_con, 1), n) if self.n_con else None
+        self._bufs = {}
+        self._a_step = z(1, self._a_lo.shape[0], n)
+        self._o_lo = torch.from_numpy(self.observation_space_base.low.astype(np.float64)).to(dev)
+        self._o_hi = torch.from_numpy(self.observation_space_base.high.astype(np.float64)).to(dev)
+        self._dev_ready = True
+
+    def _out_bufs(self, K, want_x):
+        key = (K, want_x)
+        b = self._bufs.get(key)
+        if b is None:
+            dev, n, f64 = self.device, self.n_envs, torch.float64
+            b = {"obs": torch.empty(K, self._n_obs, n, dtype=f64, device=dev),
+                 "reward": torch.empty(K, n, dtype=f64, device=dev),
+                 "done": torch.empty(K, n, dtype=torch.uint8, device=dev),
+                 "violated": torch.empty(K, n, dtype=torch.uint8, device=dev),
+                 "x": torch.empty(K, self.Nx_oracle, n, dtype=f64, device=dev) if want_x else None}
+            if len(self._bufs) > 4:
+                self._bufs.clear()
+            self._bufs[key] = b
+        return b
+
+    def _io(self, a, K, bufs, z=None) -> nat.IO:
+        io = nat.IO()
+        p = lambda t: t.data_ptr() if t is not None else None
+        io.x, io.a, io.a_save = p(self._x), p(a), p(self._a_save)
+        if self._sp_dev is not None:
+            io.sp = p(self._sp_dev)
+            nsp, n = len(self._sp_keys), self.n_envs
+            io.sp_st, io.sp_sj, io.sp_se = (nsp * n, n, 1) if self._sp_per_env else (1, self.N, 0)
+        if self._d_dev is not None:
+            io.dist = p(self._d_dev)
+            nd, n = len(self._d_keys), self.n_envs
+            io.d_st, io.d_sj, io.d_se = (nd * n, n, 1) if self._d_per_env else (1, self.N, 0)
+        io.z, io.tail = p(z), p(self._tail)
+        io.x_traj, io.obs, io.reward = p(bufs["x"]), p(bufs["obs"]), p(bufs["reward"])
+        io.done, io.violated = p(bufs["done"]), p(bufs["violated"])
+        if self._cons is not None:
+            io.g0 = p(self._cons[0])
+            io.g = self._cons[self.t + 1].data_ptr() if self.t + 1 < self.N else None
+        io.done_state, io.status, io.h_carry, io.n_rhs = p(self._done_state), p(self._status), p(self._h_carry), p(self._n_rhs)
+        return io
+
+    # ------------------------------------------------------------------ reset (pcgym.py:263-349)
+    def reset(self, seed: int = 0, **kwargs):
+        self._ensure_device()
+        self.t = 0
+        nx, n = self.Nx_oracle, self.n_envs
+        x0 = self._x0_dev.clone()
+        gen = torch.Generator(device=self.device)
+        gen.manual_seed(self.seed * 1000003 + int(seed) + self.env_id0)
+        if self.uncertainty_percentages is not None and "x0" in self.uncertainty_percentages:
+            for idx, unc in enumerate(self.uncertainty_percentages["x0"]):         # iterates keys, as :286-288
+                x0[idx] = self._perturb(x0[idx], float(unc), gen)
+        self._x.copy_(x0[:nx])
+        parts = [x0]                                                               # [x | SP slots of x0]
+        if self.disturbance_active and self._d_keys:
+            d0 = self._d_dev[0] if self._d_per_env else self._d_dev[:, 0:1].expand(-1, n)
+            parts.append(d0)
+        if self.uncertainty:
+            rows = []
+            for name in self._unc_names:
+                base = torch.full((n,), float(self.original_param_values[name]), dtype=torch.float64, device=self.device)
+                if self.uncertainty_percentages is not None:
+                    rows.append(self._perturb(base, float(self.uncertainty_percentages[name]), gen))
+                else:
+                    vals = torch.as_tensor(_np(self.empirical_distribution[name]), device=self.device)
+                    rows.append(vals[torch.randint(len(vals), (n,), generator=gen, device=self.device)])
+            self._tail.copy_(torch.stack(rows))
+            parts.append(self._tail)
+        if self.a_delta:
+            self.a_save_init = _np(self.a_0).reshape(-1)
+            self._a_save.copy_(torch.as_tensor(self.a_save_init, device=self.device)[:, None].expand(-1, n))
+        self._state0 = torch.cat(parts, dim=0)                                     # [n_obs, n]
+        self._done_state.zero_()
+        self._status.zero_()
+        self._h_carry.zero_()
+        self._n_rhs.zero_()
+        if self._cons is not None:
+            self._cons.zero_()
+        self.done = False
+        obs = self._state0
+        if self.normalise_o:
+            obs = 2 * (obs - self._o_lo[:, None]) / (self._o_hi[:, None] - self._o_lo[:, None]) - 1
+        else:
+            obs = obs.clone()
+        self.info["obs"] = obs.T.clone()
+        if self.partial_observation:
+            names = self.model.info()["states"]
+            for i in range(nx):
+                if names[i] not in self.partial_observation:
+                    obs[i] = 0
+        self._last_obs = obs
+        self.info["r_init"] = 0
+        if self._cons is not None:
+            self.info["cons_info"] = self._cons.permute(1, 0, 2)
+        self._numpy_mode = False
+        return (self._single(obs) if self.n_envs == 1 else obs.T), self.info
+
+    def _perturb(self, value, pct, gen):                                           # pcgym.py:255-261
+        if self.distribution == "uniform":
+            u = torch.rand(value.shape, generator=gen, device=self.device, dtype=torch.float64) * 2 - 1
+            return value * (1 + u * pct)
+        if self.distribution == "normal":
+            return value + torch.randn(value.shape, generator=gen, device=self.device, dtype=torch.float64) * pct * value
+        raise UnboundLocalError("distribution must be 'uniform' or 'normal'")
+
+    @staticmethod
+    def _single(t):
+        return t[:, 0].detach().cpu().numpy().copy()
+
+    # ------------------------------------------------------------------ step (pcgym.py:350-500)
+    def step(self, action, z=None):
+        if not self._dev_ready:
+            raise RuntimeError("call reset() before step()")
+        if self.t >= self.N - 1:
+            raise IndexError(f"episode finished: t = {self.t}, N = {self.N} (list index out of range)")
+        n, nu_a = self.n_envs, self._a_lo.shape[0]
+        numpy_in = not isinstance(action, torch.Tensor)
+        a = torch.as_tensor(np.asarray(action, dtype=np.float64)) if numpy_in else action
+        a = a.to(device=self.device, dtype=torch.float64, non_blocking=True)
+        if a.ndim <= 1:
+            if n != 1 and a.numel() != n * nu_a:
+                raise ValueError(f"action must have shape [{n}, {nu_a}]")
+            a = a.reshape(n, nu_a)
+        if a.shape != (n, nu_a):
+            raise ValueError(f"action must have shape [{n}, {nu_a}], got {tuple(a.shape)}")
+        self._a_step[0].copy_(a.T)
+        if z is not None:                                    # externally supplied N(0,1) draws, [n_envs, nx]
+            z = torch.as_tensor(np.asarray(z, dtype=np.float64)) if not isinstance(z, torch.Tensor) else z
+            z = z.to(device=self.device, dtype=torch.float64).reshape(n, self.Nx_oracle).T.contiguous()[None]
+        out = self._launch(self._a_step, 1, want_x=False, z=z)
+        obs_soa, r, done, violated = out["obs"][0], out["reward"][0], out["done"][0], out["violated"][0]
+        if self._copy_outputs:
+            obs_soa, r = obs_soa.clone(), r.clone()
+        self._last_obs = obs_soa
+        self.info["obs"] = obs_soa.T
+        self.info["violated"] = violated.bool()
+        self.info["status"] = self._status
+        if self.custom_reward:
+            r = self._custom_reward(obs_soa, a, violated.bool())
+        if n == 1 and numpy_in:
+            self.done = bool(done.item())
+            return self._single(obs_soa), float(r.item()) if isinstance(r, torch.Tensor) else float(r), self.done, False, self.info
+        done_b = done.bool()
+        self.done = done_b
+        return obs_soa.T, r, done_b, torch.zeros_like(done_b), self.info
+
+    def _custom_reward(self, obs_soa, a, violated):
+        raise NotImplementedError(
+            "custom_reward is a Python callable; pass a torch-vectorised function via "
+            "env_params['custom_reward_torch'] (obs_phys [n,Nx], uk [n,Nu], violated [n]) -> [n]")
+
+    # ------------------------------------------------------------------ rollout: K intervals, one launch
+    def rollout(self, actions, z=None, want_x=True):
+        """actions: [K, nu_a, n_envs] (struct-of-arrays, preferred) or [K, n_envs, nu_a]; device or host tensor.
+        Returns SoA tensors: obs [K, Nx, n], reward [K, n], done/violated [K, n] (uint8), x [K, nx, n]."""
+        if not self._dev_ready:
+            raise RuntimeError("call reset() before rollout()")
+        n, nu_a = self.n_envs, self._a_lo.shape[0]
+        a = actions if isinstance(actions, torch.Tensor) else torch.as_tensor(np.asarray(actions, dtype=np.float64))
+        if a.ndim != 3:
+            raise ValueError("actions must be [K, nu_a, n_envs]")
+        if a.shape[1:] != (nu_a, n):
+            if a.shape[1:] == (n, nu_a):
+                a = a.permute(0, 2, 1)
+            else:
+                raise ValueError(f"actions must be [K, {nu_a}, {n}] (or [K, {n}, {nu_a}]), got {tuple(a.shape)}")
+        a = a.to(device=self.device, dtype=torch.float64, non_blocking=True).contiguous()
+        K = a.shape[0]
+        if self.t + K > self.N - 1:
+            raise IndexError(f"rollout of {K} steps from t = {self.t} exceeds the episode (N - 1 = {self.N - 1} steps)")
+        if z is not None:
+            z = z.to(device=self.device, dtype=torch.float64).contiguous()
+            if z.shape != (K, self.Nx_oracle, n):
+                raise ValueError(f"z must be [K, {self.Nx_oracle}, {n}]")
+        return self._launch(a, K, want_x=want_x, z=z)
+
+    def _launch(self, a, K, want_x, z=None):
+        d = self._desc
+        if d.noise == nat.NOISE["external"] and z is None:
+            raise ValueError("noise_mode='external' needs the standard normals `z`")
+        bufs = self._out_bufs(K, want_x)
+        io = self._io(a, K, bufs, z)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        with torch.cuda.device(self.device):
+            nat.check(nat.lib().pcg_rollout(ctypes.byref(d), ctypes.byref(io), self.n_envs, self.t, K,
+                                            ctypes.c_void_p(stream)))
+        self.t += K
+        return bufs
+
+    def rewind(self, t: int = 0):
+        """Begin a new episode from the CURRENT device state: only the time index and the sticky done flag
+        are cleared (no x0 copy, no allocation).  Continuing-task rollouts and the benchmark use this."""
+        if not self._dev_ready:
+            raise RuntimeError("call reset() before rewind()")
+        self.t = int(t)
+        self._done_state.zero_()
+        self.done = False
+
+    # ------------------------------------------------------------------ reference attributes
+    @property
+    def obs(self):
+        return self._last_obs.T if self.n_envs > 1 else self._single(self._last_obs)
+
+    @property
+    def state(self):
+        """Physical state vector [x | SP[t-1] | disturbances(t) | uncertain params] (pcgym.py:284-316, 409-438)."""
+        if self.t == 0:
+            s = self._state0.clone()
+        else:
+            parts = [self._x]
+            n = self.n_envs
+            if self._sp_dev is not None:
+                parts.append(self._sp_dev[self.t - 1] if self._sp_per_env else self._sp_dev[:, self.t - 1: self.t].expand(-1, n))
+            if self._d_dev is not None:
+                parts.append(self._d_dev[self.t] if self._d_per_env else self._d_dev[:, self.t: self.t + 1].expand(-1, n))
+            if self._tail is not None:
+                parts.append(self._tail)
+            s = torch.cat(parts, dim=0)
+        return s.T if self.n_envs > 1 else self._single(s)
+
+    @property
+    def a_save(self):
+        if not self.a_delta:
+            raise AttributeError("a_save")
+        if not self._dev_ready:
+            return self.a_0
+        return self._a_save.T if self.n_envs > 1 else self._single(self._a_save)
+
+    @property
+    def status(self):
+        return self._status
+
+    @property
+    def rhs_evaluations(self):
+        return self._n_rhs
+
+    def close(self):
+        self._bufs = {}

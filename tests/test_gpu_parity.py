@@ -1,0 +1,343 @@
+"""CUDA path vs oracle / golden fixtures.  Everything here calls the kernels through the C ABI
+(pcgym_b200.make_env -> ctypes -> libpcgym_b200.so).  Tolerance: north-star rtol 1e-6 on fp64
+trajectories; tighter where both sides are converged."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import cases
+from oracle import integrate as oint
+from oracle import rhs as orhs
+
+pytestmark = pytest.mark.gpu
+
+TIGHT = {"scheme": "dopri5", "adaptive": False, "n_sub": 48}       # converged fixed-step setting (extraction is stiff)
+HEADLINE = {"scheme": "tsit5", "adaptive": False, "n_sub": 1}      # what bench.py times
+
+
+def _env(params, **over):
+    from pcgym_b200 import make_env
+    p = dict(params)
+    p.update(over)
+    return make_env(p)
+
+
+def rel(a, b, floor=1e-12):
+    a, b = np.asarray(a, float), np.asarray(b, float)
+    return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), floor))) if a.size else 0.0
+
+
+# ----------------------------------------------------------------------------- step semantics vs reference fixtures
+@pytest.mark.parametrize("name", list(cases.CASES))
+def test_step_cases_match_reference_fixture(name, golden_dir):
+    g = np.load(os.path.join(golden_dir, f"step_{name}.npz"))
+    params = cases.CASES[name]()
+    n_sub = 400 if name == "extraction" else 48
+    env = _env(params, noise_mode="external", integrator=dict(TIGHT, n_sub=n_sub))
+    obs0, info = env.reset()
+    assert isinstance(obs0, np.ndarray) and obs0.shape == g["obs0"].shape
+    np.testing.assert_allclose(obs0, g["obs0"], rtol=1e-12, atol=1e-12)
+    noisy = bool(params.get("noise", False))
+    K = g["actions"].shape[0]
+    for k in range(K):
+        z = np.nan_to_num(g["z"][k], nan=0.0)[None] if noisy else None
+        obs, r, done, trunc, info = env.step(g["actions"][k].copy(), z=z)
+        assert isinstance(obs, np.ndarray) and isinstance(r, float) and isinstance(done, bool) and trunc is False
+        np.testing.assert_allclose(env.state, g["state"][k], rtol=2e-8, atol=1e-11, err_msg=f"{name} state {k}")
+        np.testing.assert_allclose(obs, g["obs"][k], rtol=5e-7, atol=5e-8, err_msg=f"{name} obs {k}")
+        np.testing.assert_allclose(r, g["reward"][k], rtol=1e-6, atol=1e-9, err_msg=f"{name} reward {k}")
+        assert done == bool(g["done"][k]), f"{name} done {k}"
+        if env.a_delta:
+            np.testing.assert_allclose(env.a_save, g["a_save"][k], rtol=1e-12)
+    if "cons_info" in g.files:
+        ci = info["cons_info"].cpu().numpy()
+        np.testing.assert_allclose(ci, g["cons_info"], rtol=1e-6, atol=1e-7)
+    assert int(env.status.max()) == 0
+    with pytest.raises(IndexError):
+        env.step(g["actions"][0])
+
+
+@pytest.mark.parametrize("name", ["cstr_dist_cons", "four_tank", "crystallization", "extraction"])
+def test_rollout_equals_repeated_steps_bitwise(name, golden_dir):
+    g = np.load(os.path.join(golden_dir, f"step_{name}.npz"))
+    params = cases.CASES[name]()
+    n = 64
+    rng = np.random.default_rng(3)
+    acts = torch.as_tensor(rng.uniform(-1, 1, (g["actions"].shape[0], g["actions"].shape[1], n)))
+    e1 = _env(params, n_envs=n, integrator=HEADLINE, seed=5)
+    e2 = _env(params, n_envs=n, integrator=HEADLINE, seed=5)
+    e1.reset(); e2.reset()
+    out = e1.rollout(acts)
+    for k in range(acts.shape[0]):
+        obs, r, done, trunc, info = e2.step(acts[k].T.cuda())
+        assert torch.equal(obs.T, out["obs"][k]), f"obs step {k}"
+        assert torch.equal(r, out["reward"][k])
+        assert torch.equal(done, out["done"][k].bool())
+    assert torch.equal(e1._x, e2._x)
+    if e1.n_con:
+        assert torch.equal(e1.info["cons_info"], e2.info["cons_info"])
+
+
+# ----------------------------------------------------------------------------- golden do-mpc trajectories through CUDA
+@pytest.mark.parametrize("model", ["cstr", "four_tank", "multistage_extraction", "crystallization", "biofilm_reactor"])
+def test_golden_trajectories_cuda(model, golden_dir):
+    """Every stored transition x[:, i] = Phi(x[:, i-1], u[:, i]) of the reference's shipped do-mpc data
+     is replayed as one env of a batch, one step each, physical-unit actions."""
+    d = np.load(os.path.join(golden_dir, f"traj_{model}.npz"))
+    x, u, dt = d["x"], d["u"], float(d["dt"])
+    xin, uin, want = x[:, 1:-1], u[:, 2:], x[:, 2:]
+    n = xin.shape[1]
+    meta = orhs.MODELS[model]
+    sp_key = meta["states"][0]
+    params = {
+        "model": model, "N": 4, "tsim": 4 * dt, "n_envs": n,
+        "SP": {sp_key: [0.0] * 4},
+        "x0": np.concatenate([xin.T, np.zeros((n, 1))], axis=1),
+        "a_space": {"low": np.full(uin.shape[0], -1.0), "high": np.ones(uin.shape[0])},
+        "o_space": {"low": -np.ones(x.shape[0] + 1), "high": np.ones(x.shape[0] + 1)},
+        "normalise_a": False, "normalise_o": False,
+        "integrator": {"scheme": "tsit5", "adaptive": True, "rtol": 1e-10, "atol": 1e-12},
+    }
+    env = _env(params)
+    env.reset()
+    obs, r, done, trunc, info = env.step(torch.as_tensor(uin.T.copy()))
+    got = obs[:, : x.shape[0]].T.cpu().numpy()
+    assert rel(got, want) < 5e-8, rel(got, want)
+    assert int(env.status.max()) == 0
+
+
+# ----------------------------------------------------------------------------- batch parity vs the vectorised oracle
+BATCH = {
+    "cstr": dict(x0=[0.8, 330.0], a=([295.0], [302.0]), dt=0.25, jitter=0.02),
+    "first_order_system": dict(x0=[0.5], a=([0.0], [10.0]), dt=0.1, jitter=0.9),
+    "four_tank": dict(x0=[0.141, 0.112, 0.072, 0.42], a=([0.1, 0.1], [10.0, 10.0]), dt=1000 / 60, jitter=0.1),
+    "multistage_extraction": dict(x0=[0.55, 0.3, 0.45, 0.25, 0.4, 0.20, 0.35, 0.15, 0.25, 0.1], a=([5.0, 10.0], [500.0, 1000.0]), dt=1.0, jitter=0.05),
+    "crystallization": dict(x0=[1478.00986666666, 22995.8230590611, 1800863.24079725, 248516167.940593, 0.15861523304, 0.5, 15.0], a=([10.0], [40.0]), dt=1.0, jitter=0.01),
+    "biofilm_reactor": dict(x0=[11.0, 5.3, 3.7, 480.0] * 4, a=([0, 1, 0.05, 0.05, 0.05], [10, 30, 1, 1, 1]), dt=2.0, jitter=0.02),
+}
+
+
+def batch_setup(model, n, K, seed=0):
+    b = BATCH[model]
+    rng = np.random.default_rng(seed)
+    nx = len(b["x0"])
+    x0 = np.array(b["x0"])[None] * (1 + b["jitter"] * rng.uniform(-1, 1, (n, nx)))
+    meta = orhs.MODELS[model]
+    key = meta["states"][min(1, nx - 1)]
+    sp = np.linspace(0.5, 1.5, K + 1) * b["x0"][meta["states"].index(key)]
+    lo, hi = np.array(b["a"][0], float), np.array(b["a"][1], float)
+    params = {
+        "model": model, "N": K + 1, "tsim": (K + 1) * b["dt"], "n_envs": n,
+        "SP": {key: list(sp)}, "r_scale": {key: 3.0},
+        "x0": np.concatenate([x0, np.full((n, 1), sp[0])], axis=1),
+        "a_space": {"low": lo, "high": hi},
+        "o_space": {"low": np.concatenate([0.5 * np.array(b["x0"]), [0.0]]), "high": np.concatenate([1.5 * np.array(b["x0"]), [2 * sp.max()]])},
+    }
+    acts = rng.uniform(-1, 1, (K, len(lo), n))
+    return params, x0, acts, key, sp
+
+
+def oracle_batch(model, params, x0, acts, key, sp, n_sub):
+    """Vectorised restatement of the step for SP-reward, noise-free, unconstrained batches."""
+    lo, hi = params["a_space"]["low"], params["a_space"]["high"]
+    dt = params["tsim"] / params["N"]
+    meta = orhs.MODELS[model]
+    si = meta["states"].index(key)
+    x = x0.T.copy()
+    xs, rs = [], []
+    for k in range(acts.shape[0]):
+        u = (acts[k] + 1) * ((hi - lo) / 2)[:, None] + lo[:, None]
+        x = oint.advance_dense(model, x, u, dt, n_sub=n_sub)
+        xs.append(x.copy())
+        rs.append(-((x[si] - sp[k + 1]) ** 2) * 3.0)
+    return np.stack(xs), np.stack(rs)
+
+
+@pytest.mark.parametrize("model,n_sub_oracle,integ,tol", [
+    ("cstr", 32, TIGHT, 1e-9),
+    ("first_order_system", 32, TIGHT, 1e-9),
+    ("four_tank", 32, TIGHT, 1e-9),
+    ("crystallization", 64, TIGHT, 1e-8),
+    ("biofilm_reactor", 64, TIGHT, 1e-8),
+    ("multistage_extraction", 512, dict(TIGHT, n_sub=400), 1e-8),
+    ("cstr", 32, {"scheme": "tsit5", "adaptive": True, "rtol": 1e-8, "atol": 1e-8}, 1e-6),
+    ("four_tank", 32, {"scheme": "dopri5", "adaptive": True, "rtol": 1e-8, "atol": 1e-10}, 1e-6),
+    ("multistage_extraction", 512, {"scheme": "tsit5", "adaptive": True, "rtol": 1e-8, "atol": 1e-10}, 1e-6),
+    ("crystallization", 64, {"scheme": "tsit5", "adaptive": True, "rtol": 1e-9, "atol": 1e-12}, 1e-6),
+    ("cstr", 32, {"scheme": "rk4", "n_sub": 16}, 1e-8),
+])
+def test_batch_rollout_vs_oracle(model, n_sub_oracle, integ, tol):
+    n, K = 2048, 12
+    params, x0, acts, key, sp = batch_setup(model, n, K)
+    env = _env(params, integrator=integ)
+    env.reset()
+    out = env.rollout(torch.as_tensor(acts))
+    xs, rs = oracle_batch(model, params, x0, acts, key, sp, n_sub_oracle)
+    got_x = out["x"].cpu().numpy()
+    assert rel(got_x, xs) < tol, (model, rel(got_x, xs))
+    np.testing.assert_allclose(out["reward"].cpu().numpy(), rs, rtol=max(tol * 1e3, 1e-6), atol=1e-9 * np.abs(rs).max())
+    # observation = normalised [x | SP[t]]
+    lo, hi = params["o_space"]["low"], params["o_space"]["high"]
+    want_obs = 2 * (np.concatenate([xs, np.broadcast_to(sp[:K, None, None], (K, 1, n))], axis=1) - lo[None, :, None]) / (hi - lo)[None, :, None] - 1
+    np.testing.assert_allclose(out["obs"].cpu().numpy(), want_obs, rtol=0, atol=max(tol * 10, 1e-9))
+    assert int(env.status.max()) == 0
+    assert out["done"][-1].all() and not out["done"][:-1].any()
+
+
+def test_headline_config_full_size_rtol_1e6():
+    """BASELINE config 3 at full size: 65 536 CSTR envs x 99 steps with the integrator bench.py times
+    (Tsit5, one step per control interval) against a converged oracle: north-star rtol 1e-6."""
+    import bench
+    params, acts = bench.cstr_headline(n_envs=65536, device="cuda", seed=0)
+    params = dict(params, noise=False)
+    env = _env(params)
+    env.reset()
+    out = env.rollout(acts)
+    x0 = params["x0"][:, :2].cpu().numpy().T.copy()
+    a = acts.cpu().numpy()
+    x = x0
+    worst = 0.0
+    for k in range(a.shape[0]):
+        u = (a[k] + 1) * 3.5 + 295.0
+        x = oint.advance_dense("cstr", x, u, 0.25, n_sub=16)
+        worst = max(worst, rel(out["x"][k].cpu().numpy(), x))
+    assert worst < 1e-6, worst
+    assert int(env.status.max()) == 0
+    # violated flag and penalty are consistent with the stored constraint values
+    g = env.info["cons_info"][:, 1:, :]
+    v = (g > 0).any(dim=0)
+    assert torch.equal(v, out["violated"].bool())
+
+
+# ----------------------------------------------------------------------------- noise
+def philox_py(ctr, key):
+    M0, M1, W0, W1 = 0xD2511F53, 0xCD9E8D57, 0x9E3779B9, 0xBB67AE85
+    c, k = list(ctr), list(key)
+    for _ in range(10):
+        p0, p1 = M0 * c[0], M1 * c[2]
+        c = [(p1 >> 32) ^ c[1] ^ k[0], p1 & 0xFFFFFFFF, (p0 >> 32) ^ c[3] ^ k[1], p0 & 0xFFFFFFFF]
+        k = [(k[0] + W0) & 0xFFFFFFFF, (k[1] + W1) & 0xFFFFFFFF]
+    return c
+
+
+def test_philox_known_answers_host_model():
+    # Random123 kat_vectors, philox4x32-10
+    assert philox_py([0, 0, 0, 0], [0, 0]) == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
+    assert philox_py([0xffffffff] * 4, [0xffffffff] * 2) == [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
+    assert philox_py([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], [0xa4093822, 0x299f31d0]) == \
+        [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]
+
+
+def test_device_noise_is_philox_boxmuller():
+    """z recovered from the kernel's noisy observation equals Philox4x32-10 + Box-Muller for (seed, env, t)."""
+    params = cases.cstr_basic()
+    seed, id0, n = 0x1234567_89ABCDEF, 1000, 8
+    env = _env(params, n_envs=n, seed=seed, env_id0=id0, normalise_o=False, integrator=HEADLINE)
+    env.reset()
+    a = torch.zeros(3, 1, n, dtype=torch.float64)
+    out = env.rollout(a)
+    pct = 0.001
+    for k in range(3):
+        x = out["x"][k].cpu().numpy()
+        z = (out["obs"][k, :2].cpu().numpy() - x) / (x * pct)
+        for e in range(n):
+            gid = id0 + e
+            r = philox_py([gid & 0xFFFFFFFF, gid >> 32, k + 1, 0], [seed & 0xFFFFFFFF, seed >> 32])
+            u0 = (((r[1] << 32 | r[0]) >> 11) + 0.5) * 2.0 ** -53
+            u1 = (((r[3] << 32 | r[2]) >> 11) + 0.5) * 2.0 ** -53
+            rad = np.sqrt(-2 * np.log(u0))
+            np.testing.assert_allclose(z[:, e], [rad * np.cos(2 * np.pi * u1), rad * np.sin(2 * np.pi * u1)], rtol=0, atol=2e-9)
+
+
+@pytest.mark.parametrize("mode", ["philox", "philox_f32"])
+def test_noise_statistics_and_shard_invariance(mode):
+    params = cases.cstr_basic()
+    n, K = 32768, 8
+    a = torch.zeros(K, 1, n, dtype=torch.float64)
+    env = _env(params, n_envs=n, seed=11, noise_mode=mode, normalise_o=False, integrator=HEADLINE)
+    env.reset()
+    out = env.rollout(a)
+    x = out["x"]
+    z = ((out["obs"][:, :2] - x) / (x * 0.001)).cpu().numpy().ravel()
+    assert abs(z.mean()) < 4 / np.sqrt(z.size)
+    assert abs(z.std() - 1) < 0.01
+    assert abs((z ** 4).mean() - 3) < 0.1                      # kurtosis of a Gaussian
+    assert abs(np.corrcoef(z[:-1], z[1:])[0, 1]) < 0.01
+    # the second half of the batch run as its own shard (env_id0 offset) sees identical draws
+    half = _env(params, n_envs=n // 2, env_id0=n // 2, seed=11, noise_mode=mode, normalise_o=False, integrator=HEADLINE)
+    half.reset()
+    out2 = half.rollout(a[:, :, n // 2:])
+    assert torch.equal(out2["obs"], out["obs"][:, :, n // 2:])
+    # different seed -> different draws
+    other = _env(params, n_envs=n, seed=12, noise_mode=mode, normalise_o=False, integrator=HEADLINE)
+    other.reset()
+    assert not torch.equal(other.rollout(a)["obs"], out["obs"])
+
+
+# ----------------------------------------------------------------------------- robustness
+def test_biofilm_pole_sets_status_and_terminates():
+    """Documented x0 runs into the Monod pole S2 = -K2: the kernel must finish, flag the
+    affected envs and leave healthy envs untouched."""
+    p = cases.biofilm()
+    n = 256
+    x0 = np.tile(np.array([11.0, 5.3, 3.7, 480.0] * 4 + [1.5]), (n, 1))
+    x0[::2] = np.array([2, 0.1, 10, 0.1] * 4 + [1.5])          # every other env starts at the documented x0
+    env = _env(p, n_envs=n, x0=x0, N=40, tsim=80, SP={"S2_A": [1.5] * 40},
+               integrator={"scheme": "dopri5", "adaptive": True, "rtol": 1e-8, "atol": 1e-10, "max_steps": 300})
+    env.reset()
+    out = env.rollout(torch.zeros(39, 5, n, dtype=torch.float64))
+    torch.cuda.synchronize()
+    st = env.status.cpu().numpy()
+    assert (st[1::2] == 0).all()
+    assert (st[0::2] != 0).all()
+    assert torch.isfinite(out["x"][:, :, 1::2]).all()
+
+
+def test_step_cap_flag():
+    params, x0, acts, key, sp = batch_setup("multistage_extraction", 64, 4)
+    env = _env(params, integrator={"scheme": "dopri5", "adaptive": True, "rtol": 1e-8, "atol": 1e-10, "max_steps": 3})
+    env.reset()
+    env.rollout(torch.as_tensor(acts))
+    assert (env.status.cpu().numpy() & 2).all()
+
+
+def test_per_env_setpoints_and_disturbances():
+    p = cases.cstr_dist_cons()
+    n, N = 16, p["N"]
+    rng = np.random.default_rng(0)
+    sp = rng.uniform(0.8, 0.9, (n, N))
+    ti = rng.uniform(340, 360, (n, N))
+    caf = np.asarray(p["disturbances"]["Caf"])
+    acts = rng.uniform(-1, 1, (N - 1, 1, n))
+    env = _env(p, n_envs=n, SP={"Ca": sp}, disturbances={"Ti": ti, "Caf": caf}, integrator=TIGHT)
+    env.reset()
+    out = env.rollout(torch.as_tensor(acts))
+    x = np.tile(np.array([[0.8], [330.0]]), (1, n))
+    for k in range(N - 1):
+        u = np.stack([(acts[k, 0] + 1) * 3.5 + 295.0, ti[:, k + 1], np.full(n, caf[k + 1])])
+        x = oint.advance_dense("cstr", x, u, p["tsim"] / N, n_sub=32)
+        assert rel(out["x"][k].cpu().numpy(), x) < 1e-9
+        np.testing.assert_allclose(out["reward"][k].cpu().numpy() + 1000.0, -((x[0] - sp[:, k + 1]) ** 2) * 1e3, rtol=1e-6, atol=1e-9)
+        obs = out["obs"][k].cpu().numpy()
+        np.testing.assert_allclose(obs[2], 2 * (sp[:, k] - 0.8) / 0.1 - 1, atol=1e-12)
+        np.testing.assert_allclose(obs[3], 2 * (ti[:, k + 1] - 330.0) / 40.0 - 1, atol=1e-12)
+
+
+def test_uncertainty_is_observation_only():
+    p = cases.cstr_basic()
+    p.update(noise=False, uncertainty_percentages={"k0": 0.1, "x0": [0.05, 0.0, 0.0]}, distribution="uniform",
+             uncertainty_bounds={"low": np.array([6e10]), "high": np.array([8e10])})
+    n = 512
+    env = _env(p, n_envs=n, integrator=TIGHT)
+    obs, _ = env.reset()
+    assert obs.shape == (n, 4)
+    k0 = (obs[:, 3].cpu().numpy() + 1) / 2 * 2e10 + 6e10
+    assert k0.std() > 0 and np.all(np.abs(k0 / 7.2e10 - 1) <= 0.1 + 1e-12)
+    ca0 = (obs[:, 0].cpu().numpy() + 1) / 2 * 0.3 + 0.7
+    assert ca0.std() > 0 and np.all(np.abs(ca0 / 0.8 - 1) <= 0.05 + 1e-12)
+    o1, *_ = env.step(torch.zeros(n, 1, dtype=torch.float64))
+    np.testing.assert_allclose(o1[:, 3].cpu().numpy(), obs[:, 3].cpu().numpy())      # carried, never fed to the dynamics
+    x = oint.advance_dense("cstr", np.stack([ca0, np.full(n, 330.0)]), np.full((1, n), 298.5), 0.25, n_sub=32)
+    assert rel(env._x.cpu().numpy(), x) < 1e-9
