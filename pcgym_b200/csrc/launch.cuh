@@ -1,4 +1,5 @@
-// Host-side launch of rollout_kernel for one model: picks the (scheme, adaptive) instantiation.
+// Host-side launch of rollout_kernel for one model: picks the (scheme, adaptive, general) instantiation,
+// computes the derived constant block and the vector-access eligibility.
 #pragma once
 #include <cuda_runtime.h>
 
@@ -8,11 +9,40 @@ namespace pcg {
 
 using launch_fn = cudaError_t (*)(const pcg_desc&, const pcg_io&, int64_t, int, int, cudaStream_t);
 
-template <class M, class TB, bool ADAPTIVE>
+inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// 128-bit row access needs an even env count (every row then starts 16-byte aligned) and aligned bases
+inline bool vector_ok(const pcg_io& io, int64_t n) {
+  if (n % 2) return false;
+  const void* f64[] = {io.x, io.a, io.a_save, io.z, io.tail, io.x_traj, io.obs, io.reward, io.g, io.g0};
+  for (const void* p : f64)
+    if (!al16(p)) return false;
+  return (reinterpret_cast<uintptr_t>(io.done) & 1u) == 0 && (reinterpret_cast<uintptr_t>(io.violated) & 1u) == 0;
+}
+
+template <class M>
+inline bool needs_general(const pcg_desc& d) {
+  if (d.n_tail > 0 || d.nd > 0 || d.nsp > 2) return true;
+  for (int c = 0; c < d.n_con; ++c)
+    if (d.con_mask_x[c] >> M::NX) return true;
+  return false;
+}
+
+template <class M, class TB, bool ADAPTIVE, bool GENERAL>
 cudaError_t launch_one(const pcg_desc& d, const pcg_io& io, int64_t n_env, int t0, int k_steps, cudaStream_t s) {
-  const unsigned grid = static_cast<unsigned>((n_env + kBlock - 1) / kBlock);
-  rollout_kernel<M, TB, ADAPTIVE><<<grid, kBlock, 0, s>>>(d, io, n_env, t0, k_steps);
+  constexpr int EPT = ADAPTIVE ? 1 : M::EPT;
+  const int64_t threads = (n_env + EPT - 1) / EPT;
+  const unsigned grid = static_cast<unsigned>((threads + kBlock - 1) / kBlock);
+  const Derived<M, TB> dv = make_derived<M, TB>(d);
+  const int vec = (EPT == 2 && vector_ok(io, n_env)) ? 1 : 0;
+  rollout_kernel<M, TB, ADAPTIVE, GENERAL, EPT><<<grid, kBlock, 0, s>>>(d, io, dv, n_env, t0, k_steps, vec);
   return cudaGetLastError();
+}
+
+template <class M, class TB, bool ADAPTIVE>
+cudaError_t launch_g(const pcg_desc& d, const pcg_io& io, int64_t n_env, int t0, int k_steps, cudaStream_t s) {
+  return needs_general<M>(d) ? launch_one<M, TB, ADAPTIVE, true>(d, io, n_env, t0, k_steps, s)
+                             : launch_one<M, TB, ADAPTIVE, false>(d, io, n_env, t0, k_steps, s);
 }
 
 template <class M>
@@ -20,13 +50,13 @@ cudaError_t launch_model(const pcg_desc& d, const pcg_io& io, int64_t n_env, int
   const bool adaptive = (d.flags & PCG_F_ADAPTIVE) != 0;
   switch (d.scheme) {
     case PCG_SCHEME_RK4:
-      return launch_one<M, Rk4, false>(d, io, n_env, t0, k_steps, s);
+      return launch_g<M, Rk4, false>(d, io, n_env, t0, k_steps, s);
     case PCG_SCHEME_DOPRI5:
-      return adaptive ? launch_one<M, Dopri5, true>(d, io, n_env, t0, k_steps, s)
-                      : launch_one<M, Dopri5, false>(d, io, n_env, t0, k_steps, s);
+      return adaptive ? launch_g<M, Dopri5, true>(d, io, n_env, t0, k_steps, s)
+                      : launch_g<M, Dopri5, false>(d, io, n_env, t0, k_steps, s);
     case PCG_SCHEME_TSIT5:
-      return adaptive ? launch_one<M, Tsit5, true>(d, io, n_env, t0, k_steps, s)
-                      : launch_one<M, Tsit5, false>(d, io, n_env, t0, k_steps, s);
+      return adaptive ? launch_g<M, Tsit5, true>(d, io, n_env, t0, k_steps, s)
+                      : launch_g<M, Tsit5, false>(d, io, n_env, t0, k_steps, s);
   }
   return cudaErrorInvalidValue;
 }

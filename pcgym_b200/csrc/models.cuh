@@ -15,11 +15,12 @@
 // converged solution of the reference RHS to rtol 1e-6, and the regrouping perturbs
 // results at the 1e-15 level.
 #pragma once
+#include <cmath>
 #include <cstdint>
 
-namespace pcg {
+#include "fastmath.cuh"
 
-#define PCG_DEV __device__ __forceinline__
+namespace pcg {
 
 // ---------------------------------------------------------------------------------------
 // cstr -- model_classes.py:23-62
@@ -27,7 +28,7 @@ namespace pcg {
 struct Cstr {
   static constexpr int NX = 2, NU = 1, ND = 2, NP = 10;
   struct P { double thru, k0, neg_ear, c_heat, c_cool; };
-  PCG_DEV static P make(const double* th) {
+  PCG_HD static P make(const double* th) {
     P p;
     p.thru = th[0] / th[1];                       // q / V
     p.k0 = th[6];
@@ -37,11 +38,13 @@ struct Cstr {
     return p;
   }
   static constexpr int d_param[ND] = {8, 9};      // theta index of each disturbance default
+  static constexpr int EPT = 2;                   // environments per thread (ILP 2 on the FP64 pipe)
+  static constexpr int MIN_BLOCKS = 4;
   PCG_DEV static void rhs(const P& p, const double* x, const double* u, double* dx) {
     const double ca = x[0], T = x[1];
     const double Tc = u[0], Ti = u[1], Caf = u[2];
-    const double rate = p.k0 * exp(p.neg_ear / T) * ca;          // :52
-    dx[0] = fma(p.thru, Caf - ca, -rate);                        // :53
+    const double rate = p.k0 * exp_sat(p.neg_ear * rcp_nr(T)) * ca;      // :52
+    dx[0] = fma(p.thru, Caf - ca, -rate);                                // :53
     dx[1] = fma(p.thru, Ti - T, fma(p.c_heat, rate, p.c_cool * (Tc - T)));   // :54-58
   }
 };
@@ -51,8 +54,9 @@ struct Cstr {
 struct FirstOrder {
   static constexpr int NX = 1, NU = 1, ND = 0, NP = 2;
   struct P { double K, inv_tau; };
-  PCG_DEV static P make(const double* th) { return P{th[0], 1.0 / th[1]}; }
+  PCG_HD static P make(const double* th) { return P{th[0], 1.0 / th[1]}; }
   static constexpr int d_param[1] = {0};
+  static constexpr int EPT = 2, MIN_BLOCKS = 8;
   PCG_DEV static void rhs(const P& p, const double* x, const double* u, double* dx) {
     dx[0] = fma(p.K, u[0], -x[0]) * p.inv_tau;                   // :322
   }
@@ -66,7 +70,7 @@ struct Extraction {
   static constexpr int NSTAGE = 5;
   static constexpr int NX = 2 * NSTAGE, NU = 2, ND = 2, NP = 7;
   struct P { double inv_vl, inv_vg, inv_m, kla_vl, expo; bool square; };
-  PCG_DEV static P make(const double* th) {
+  PCG_HD static P make(const double* th) {
     P p;
     p.inv_vl = 1.0 / th[0];
     p.inv_vg = 1.0 / th[1];
@@ -77,6 +81,7 @@ struct Extraction {
     return p;
   }
   static constexpr int d_param[ND] = {5, 6};
+  static constexpr int EPT = 1, MIN_BLOCKS = 4;
   PCG_DEV static void rhs(const P& p, const double* x, const double* u, double* dx) {
     const double L = u[0], G = u[1], X0 = u[2], Y6 = u[3];
 #pragma unroll
@@ -98,7 +103,7 @@ struct Extraction {
 struct FourTank {
   static constexpr int NX = 4, NU = 2, ND = 0, NP = 13;
   struct P { double g2, o11, o13, o22, o24, o33, o44, p11, p22, p32, p41; };
-  PCG_DEV static P make(const double* th) {
+  PCG_HD static P make(const double* th) {
     P p;
     p.g2 = 2.0 * th[0];
     const double A1 = th[9], A2 = th[10], A3 = th[11], A4 = th[12];
@@ -112,6 +117,7 @@ struct FourTank {
     return p;
   }
   static constexpr int d_param[1] = {0};
+  static constexpr int EPT = 1, MIN_BLOCKS = 4;
   PCG_DEV static void rhs(const P& p, const double* x, const double* u, double* dx) {
     const double s1 = sqrt(p.g2 * x[0]), s2 = sqrt(p.g2 * x[1]);   // NaN for h < 0, as the reference
     const double s3 = sqrt(p.g2 * x[2]), s4 = sqrt(p.g2 * x[3]);
@@ -129,10 +135,11 @@ struct FourTank {
 struct Crystallization {
   static constexpr int NX = 7, NU = 1, ND = 3, NP = 11;
   struct P { double ka, kb, kc, kd, kg, k1, k2, a, b, half_ro_alfa; };
-  PCG_DEV static P make(const double* th) {
+  PCG_HD static P make(const double* th) {
     return P{th[0], th[1], th[2], th[3], th[4], th[5], th[6], th[7], th[8], 0.5 * th[10] * th[9]};
   }
   static constexpr int d_param[ND] = {0, 4, -1};   // "UA" is not a parameter of this model
+  static constexpr int EPT = 1, MIN_BLOCKS = 4;
   PCG_DEV static void rhs(const P& p, const double* x, const double* u, double* dx) {
     const double mu0 = x[0], mu1 = x[1], mu2 = x[2], mu3 = x[3], conc = x[4];
     const double TK = u[0] + 273.15;
@@ -164,7 +171,7 @@ struct Crystallization {
 struct Biofilm {
   static constexpr int NX = 16, NU = 5, ND = 0, NP = 12;
   struct P { double inv_v, inv_va, kla, o_eq, vm1, vm2, K1, K2, KO1, KO2; };
-  PCG_DEV static P make(const double* th) {
+  PCG_HD static P make(const double* th) {
     P p;
     p.inv_v = 1.0 / th[0];
     p.inv_va = 1.0 / th[1];
@@ -174,6 +181,7 @@ struct Biofilm {
     return p;
   }
   static constexpr int d_param[1] = {0};
+  static constexpr int EPT = 1, MIN_BLOCKS = 4;
   PCG_DEV static void rhs(const P& p, const double* x, const double* u, double* dx) {
     const double F = u[0], Fr = u[1];
     const double frv = Fr * p.inv_v, fra = Fr * p.inv_va, fa = F * p.inv_va;

