@@ -162,6 +162,8 @@ def main():
     ap.add_argument("--n-envs", type=int, default=N_ENVS, help="envs per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ref-envs-per-worker", type=int, default=8)
+    ap.add_argument("--noise-mode", default="philox", choices=["philox", "philox_f32", "off"],
+                    help="experiment knob; the headline is 'philox' (fp64 Box-Muller)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -192,6 +194,10 @@ def main():
     W, K = max(args.warmup, 3), args.steps
 
     params, acts0 = cstr_headline(n_envs=n, device=dev, seed=0, env_id0=rank * n)
+    if args.noise_mode == "off":
+        params["noise"] = False
+    else:
+        params["noise_mode"] = args.noise_mode
     env = make_env(params)
     env.reset()
     # ring of action buffers so consecutive launches never re-read the same (possibly L2-resident) input

@@ -3,6 +3,8 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <cstdlib>
+
 #include "rollout_kernel.cuh"
 
 namespace pcg {
@@ -22,27 +24,42 @@ inline bool vector_ok(const pcg_io& io, int64_t n) {
 
 template <class M>
 inline bool needs_general(const pcg_desc& d) {
-  if (d.n_tail > 0 || d.nd > 0 || d.nsp > 2) return true;
+  if (d.n_tail > 0 || d.nd > 0 || d.nsp > 2 || d.n_con > 4) return true;
   for (int c = 0; c < d.n_con; ++c)
     if (d.con_mask_x[c] >> M::NX) return true;
   return false;
 }
 
-template <class M, class TB, bool ADAPTIVE, bool GENERAL>
+template <class M, class TB, bool ADAPTIVE, bool GENERAL, int EPT>
 cudaError_t launch_one(const pcg_desc& d, const pcg_io& io, int64_t n_env, int t0, int k_steps, cudaStream_t s) {
-  constexpr int EPT = ADAPTIVE ? 1 : M::EPT;
   const int64_t threads = (n_env + EPT - 1) / EPT;
   const unsigned grid = static_cast<unsigned>((threads + kBlock - 1) / kBlock);
   const Derived<M, TB> dv = make_derived<M, TB>(d);
-  const int vec = (EPT == 2 && vector_ok(io, n_env)) ? 1 : 0;
-  rollout_kernel<M, TB, ADAPTIVE, GENERAL, EPT><<<grid, kBlock, 0, s>>>(d, io, dv, n_env, t0, k_steps, vec);
+  rollout_kernel<M, TB, ADAPTIVE, GENERAL, EPT><<<grid, kBlock, 0, s>>>(d, io, dv, n_env, t0, k_steps);
   return cudaGetLastError();
+}
+
+// environments per thread: the model's preference for the lock-step fixed integrator (2 = ILP 2 and
+// 128-bit rows), 1 for the adaptive integrator (lanes take different step counts anyway).
+// PCG_EPT=1 in the environment forces one env per thread (profiling knob, read once).
+inline int ept_override() {
+  static const int v = [] { const char* e = std::getenv("PCG_EPT"); return e ? std::atoi(e) : 0; }();
+  return v;
+}
+
+template <class M, class TB, bool ADAPTIVE, bool GENERAL>
+cudaError_t launch_e(const pcg_desc& d, const pcg_io& io, int64_t n_env, int t0, int k_steps, cudaStream_t s) {
+  if constexpr (!ADAPTIVE && M::EPT == 2) {
+    if (ept_override() != 1 && vector_ok(io, n_env))
+      return launch_one<M, TB, ADAPTIVE, GENERAL, 2>(d, io, n_env, t0, k_steps, s);
+  }
+  return launch_one<M, TB, ADAPTIVE, GENERAL, 1>(d, io, n_env, t0, k_steps, s);
 }
 
 template <class M, class TB, bool ADAPTIVE>
 cudaError_t launch_g(const pcg_desc& d, const pcg_io& io, int64_t n_env, int t0, int k_steps, cudaStream_t s) {
-  return needs_general<M>(d) ? launch_one<M, TB, ADAPTIVE, true>(d, io, n_env, t0, k_steps, s)
-                             : launch_one<M, TB, ADAPTIVE, false>(d, io, n_env, t0, k_steps, s);
+  return needs_general<M>(d) ? launch_e<M, TB, ADAPTIVE, true>(d, io, n_env, t0, k_steps, s)
+                             : launch_e<M, TB, ADAPTIVE, false>(d, io, n_env, t0, k_steps, s);
 }
 
 template <class M>

@@ -27,25 +27,32 @@ namespace pcg {
 // theta: q V rho C deltaHr EA_over_R k0 UA Ti Caf       disturbances: Ti, Caf
 struct Cstr {
   static constexpr int NX = 2, NU = 1, ND = 2, NP = 10;
-  struct P { double thru, k0, neg_ear, c_heat, c_cool; };
+  struct P { double thru, ln_k0, neg_ear, c_heat, c_cool, c_T; };
   PCG_HD static P make(const double* th) {
     P p;
     p.thru = th[0] / th[1];                       // q / V
-    p.k0 = th[6];
+    p.ln_k0 = log(th[6]);                         // k0 exp(-E/T) = exp(ln k0 - E/T)
     p.neg_ear = -th[5];                           // -EA/R
     p.c_heat = (-th[4]) / (th[2] * th[3]);        // (-deltaHr) / (rho C)
     p.c_cool = th[7] / (th[2] * th[3] * th[1]);   // UA / (rho C V)
+    p.c_T = -(p.thru + p.c_cool);
     return p;
+  }
+  // per-interval constants: the input is held over the control interval, so everything that depends
+  // only on uk is hoisted out of the six RHS evaluations
+  struct Aux { double feed_c, heat0; };
+  PCG_DEV static void prep(const P& p, const double* u, Aux& a) {
+    a.feed_c = p.thru * u[2];                             // q/V Caf
+    a.heat0 = fma(p.thru, u[1], p.c_cool * u[0]);         // q/V Ti + UA/(rho C V) Tc
   }
   static constexpr int d_param[ND] = {8, 9};      // theta index of each disturbance default
   static constexpr int EPT = 2;                   // environments per thread (ILP 2 on the FP64 pipe)
   static constexpr int MIN_BLOCKS = 4;
-  PCG_DEV static void rhs(const P& p, const double* x, const double* u, double* dx) {
+  PCG_DEV static void rhs(const P& p, const Aux& a, const double* x, const double*, double* dx) {
     const double ca = x[0], T = x[1];
-    const double Tc = u[0], Ti = u[1], Caf = u[2];
-    const double rate = p.k0 * exp_sat(p.neg_ear * rcp_nr(T)) * ca;      // :52
-    dx[0] = fma(p.thru, Caf - ca, -rate);                                // :53
-    dx[1] = fma(p.thru, Ti - T, fma(p.c_heat, rate, p.c_cool * (Tc - T)));   // :54-58
+    const double rate = exp_sat(fma(p.neg_ear, rcp_nr(T), p.ln_k0)) * ca;        // :52
+    dx[0] = fma(-p.thru, ca, a.feed_c) - rate;                                   // :53
+    dx[1] = fma(p.c_heat, rate, fma(p.c_T, T, a.heat0));                         // :54-58
   }
 };
 
@@ -55,9 +62,11 @@ struct FirstOrder {
   static constexpr int NX = 1, NU = 1, ND = 0, NP = 2;
   struct P { double K, inv_tau; };
   PCG_HD static P make(const double* th) { return P{th[0], 1.0 / th[1]}; }
+  struct Aux {};
+  PCG_DEV static void prep(const P&, const double*, Aux&) {}
   static constexpr int d_param[1] = {0};
   static constexpr int EPT = 2, MIN_BLOCKS = 8;
-  PCG_DEV static void rhs(const P& p, const double* x, const double* u, double* dx) {
+  PCG_DEV static void rhs(const P& p, const Aux&, const double* x, const double* u, double* dx) {
     dx[0] = fma(p.K, u[0], -x[0]) * p.inv_tau;                   // :322
   }
 };
@@ -80,9 +89,11 @@ struct Extraction {
     p.square = (th[4] == 2.0);
     return p;
   }
+  struct Aux {};
+  PCG_DEV static void prep(const P&, const double*, Aux&) {}
   static constexpr int d_param[ND] = {5, 6};
   static constexpr int EPT = 1, MIN_BLOCKS = 4;
-  PCG_DEV static void rhs(const P& p, const double* x, const double* u, double* dx) {
+  PCG_DEV static void rhs(const P& p, const Aux&, const double* x, const double* u, double* dx) {
     const double L = u[0], G = u[1], X0 = u[2], Y6 = u[3];
 #pragma unroll
     for (int i = 0; i < NSTAGE; ++i) {
@@ -116,9 +127,11 @@ struct FourTank {
     p.p41 = ((1.0 - th[1]) * th[3]) / A4;
     return p;
   }
+  struct Aux {};
+  PCG_DEV static void prep(const P&, const double*, Aux&) {}
   static constexpr int d_param[1] = {0};
   static constexpr int EPT = 1, MIN_BLOCKS = 4;
-  PCG_DEV static void rhs(const P& p, const double* x, const double* u, double* dx) {
+  PCG_DEV static void rhs(const P& p, const Aux&, const double* x, const double* u, double* dx) {
     const double s1 = sqrt(p.g2 * x[0]), s2 = sqrt(p.g2 * x[1]);   // NaN for h < 0, as the reference
     const double s3 = sqrt(p.g2 * x[2]), s4 = sqrt(p.g2 * x[3]);
     dx[0] = fma(p.o11, s1, fma(p.o13, s3, p.p11 * u[0]));          // :906
@@ -138,9 +151,11 @@ struct Crystallization {
   PCG_HD static P make(const double* th) {
     return P{th[0], th[1], th[2], th[3], th[4], th[5], th[6], th[7], th[8], 0.5 * th[10] * th[9]};
   }
+  struct Aux {};
+  PCG_DEV static void prep(const P&, const double*, Aux&) {}
   static constexpr int d_param[ND] = {0, 4, -1};   // "UA" is not a parameter of this model
   static constexpr int EPT = 1, MIN_BLOCKS = 4;
-  PCG_DEV static void rhs(const P& p, const double* x, const double* u, double* dx) {
+  PCG_DEV static void rhs(const P& p, const Aux&, const double* x, const double* u, double* dx) {
     const double mu0 = x[0], mu1 = x[1], mu2 = x[2], mu3 = x[3], conc = x[4];
     const double TK = u[0] + 273.15;
     const double Ceq = fma(TK, fma(-0.00292874, TK, 3.579165), -686.2686);      // :1302
@@ -180,9 +195,11 @@ struct Biofilm {
     p.vm1 = th[6]; p.vm2 = th[7]; p.K1 = th[8]; p.K2 = th[9]; p.KO1 = th[10]; p.KO2 = th[11];
     return p;
   }
+  struct Aux {};
+  PCG_DEV static void prep(const P&, const double*, Aux&) {}
   static constexpr int d_param[1] = {0};
   static constexpr int EPT = 1, MIN_BLOCKS = 4;
-  PCG_DEV static void rhs(const P& p, const double* x, const double* u, double* dx) {
+  PCG_DEV static void rhs(const P& p, const Aux&, const double* x, const double* u, double* dx) {
     const double F = u[0], Fr = u[1];
     const double frv = Fr * p.inv_v, fra = Fr * p.inv_va, fa = F * p.inv_va;
 #pragma unroll

@@ -7,6 +7,8 @@
 #pragma once
 #include <cstdint>
 
+#include "fastmath.cuh"
+
 namespace pcg {
 
 __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
@@ -29,9 +31,9 @@ __device__ __forceinline__ void normal_pair_f64(uint4 r, double& z0, double& z1)
   const uint64_t b1 = (static_cast<uint64_t>(r.w) << 32) | r.z;
   const double u0 = (static_cast<double>(b0 >> 11) + 0.5) * 0x1p-53;
   const double u1 = (static_cast<double>(b1 >> 11) + 0.5) * 0x1p-53;
-  const double rad = sqrt(-2.0 * log(u0));
+  const double rad = sqrt_nr(-2.0 * log_pos(u0));      // branch-free: the two envs of a thread interleave
   double s, c;
-  sincospi(2.0 * u1, &s, &c);
+  sincospi_02(2.0 * u1, s, c);
   z0 = rad * c;
   z1 = rad * s;
 }

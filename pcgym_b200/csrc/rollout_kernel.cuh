@@ -67,35 +67,32 @@ PCG_DEV double pick(const double (&v)[N], int idx) {
 }
 
 // ------------------------------------------------------------------ row access: EPT consecutive envs
+// EPT == 2 is only launched when every row is 16-byte aligned (even n_env, aligned bases: launch.cuh),
+// so the pair is one 128-bit access; EPT == 1 is the general 64-bit path.
 template <int EPT>
-PCG_DEV void ld_row(const double* p, bool vec, const bool (&ok)[EPT], double (&v)[EPT]) {
-  if (EPT == 2 && vec) {
+PCG_DEV void ld_row(const double* p, double (&v)[EPT]) {
+  if constexpr (EPT == 2) {
     const double2 t = __ldcs(reinterpret_cast<const double2*>(p));
     v[0] = t.x;
     v[EPT - 1] = t.y;
   } else {
-#pragma unroll
-    for (int e = 0; e < EPT; ++e) v[e] = ok[e] ? __ldcs(p + e) : 1.0;
+    v[0] = __ldcs(p);
   }
 }
 template <int EPT>
-PCG_DEV void st_row(double* p, bool vec, const bool (&ok)[EPT], const double (&v)[EPT]) {
-  if (EPT == 2 && vec) {
+PCG_DEV void st_row(double* p, const double (&v)[EPT]) {
+  if constexpr (EPT == 2) {
     __stcs(reinterpret_cast<double2*>(p), make_double2(v[0], v[EPT - 1]));
   } else {
-#pragma unroll
-    for (int e = 0; e < EPT; ++e)
-      if (ok[e]) __stcs(p + e, v[e]);
+    __stcs(p, v[0]);
   }
 }
 template <int EPT>
-PCG_DEV void st_flags(uint8_t* p, bool vec, const bool (&ok)[EPT], const bool (&f)[EPT]) {
-  if (EPT == 2 && vec) {
+PCG_DEV void st_flags(uint8_t* p, const bool (&f)[EPT]) {
+  if constexpr (EPT == 2) {
     *reinterpret_cast<uchar2*>(p) = make_uchar2(f[0] ? 1 : 0, f[EPT - 1] ? 1 : 0);
   } else {
-#pragma unroll
-    for (int e = 0; e < EPT; ++e)
-      if (ok[e]) p[e] = f[e] ? 1 : 0;
+    p[0] = f[0] ? 1 : 0;
   }
 }
 
@@ -103,14 +100,13 @@ PCG_DEV void st_flags(uint8_t* p, bool vec, const bool (&ok)[EPT], const bool (&
 // The EPT environments advance in lock step: their RHS evaluations sit in one basic block so the
 // scheduler interleaves the two dependency chains.
 template <class M, class TB, int EPT>
-PCG_DEV void advance_fixed(const Derived<M, TB>& dv, double (&x)[EPT][M::NX], const double (&u)[EPT][M::NU + M::ND],
-                           int n_sub) {
+PCG_DEV void rk_step_fixed(const Derived<M, TB>& dv, const typename M::Aux (&aux)[EPT], double (&x)[EPT][M::NX],
+                           const double (&u)[EPT][M::NU + M::ND]) {
   constexpr int NX = M::NX;
-#pragma unroll 1
-  for (int s = 0; s < n_sub; ++s) {
+  {
     double k[TB::S][EPT][NX];
 #pragma unroll
-    for (int e = 0; e < EPT; ++e) M::rhs(dv.p, x[e], u[e], k[0][e]);
+    for (int e = 0; e < EPT; ++e) M::rhs(dv.p, aux[e], x[e], u[e], k[0][e]);
 #pragma unroll
     for (int i = 1; i < TB::S; ++i) {
       double xi[EPT][NX];
@@ -125,7 +121,7 @@ PCG_DEV void advance_fixed(const Derived<M, TB>& dv, double (&x)[EPT][M::NX], co
           xi[e][n] = acc;
         }
 #pragma unroll
-      for (int e = 0; e < EPT; ++e) M::rhs(dv.p, xi[e], u[e], k[i][e]);
+      for (int e = 0; e < EPT; ++e) M::rhs(dv.p, aux[e], xi[e], u[e], k[i][e]);
     }
 #pragma unroll
     for (int e = 0; e < EPT; ++e)
@@ -153,8 +149,10 @@ PCG_DEV void advance_adaptive(const Derived<M, TB>& dv, double (&x)[M::NX], cons
   constexpr int NX = M::NX, S = TB::S;
   double t = 0.0;
   double h = (h_carry > 0.0 && h_carry < dt) ? h_carry : dt;
+  typename M::Aux aux;
+  M::prep(dv.p, u, aux);
   double k0[NX];
-  M::rhs(dv.p, x, u, k0);
+  M::rhs(dv.p, aux, x, u, k0);
   ++n_rhs;
   int steps = 0;
   bool rejected = false;
@@ -179,7 +177,7 @@ PCG_DEV void advance_adaptive(const Derived<M, TB>& dv, double (&x)[M::NX], cons
           if (TB::a(i, j) != 0.0) acc = fma(dv.a[i][j], hk[j][n], acc);
         xi[n] = acc;
       }
-      M::rhs(dv.p, xi, u, k);
+      M::rhs(dv.p, aux, xi, u, k);
 #pragma unroll
       for (int n = 0; n < NX; ++n) hk[i][n] = hh * k[n];
     }
@@ -192,7 +190,7 @@ PCG_DEV void advance_adaptive(const Derived<M, TB>& dv, double (&x)[M::NX], cons
         if (TB::b(i) != 0.0) acc = fma(dv.b[i], hk[i][n], acc);
       xn[n] = acc;
     }
-    M::rhs(dv.p, xn, u, kn);                    // FSAL stage: k_{S+1} = f(x_new)
+    M::rhs(dv.p, aux, xn, u, kn);                    // FSAL stage: k_{S+1} = f(x_new)
     n_rhs += S;
     double sq = 0.0;
 #pragma unroll
@@ -229,18 +227,14 @@ PCG_DEV void advance_adaptive(const Derived<M, TB>& dv, double (&x)[M::NX], cons
 template <class M, class TB, bool ADAPTIVE, bool GENERAL, int EPT>
 __global__ void __launch_bounds__(kBlock, M::MIN_BLOCKS)
 rollout_kernel(const __grid_constant__ pcg_desc d, const __grid_constant__ pcg_io io,
-               const __grid_constant__ Derived<M, TB> dv, const int64_t n, const int t0, const int k_steps,
-               const int vec_i) {
+               const __grid_constant__ Derived<M, TB> dv, const int64_t n, const int t0, const int k_steps) {
   constexpr int NX = M::NX, NU = M::NU, ND = M::ND, NUK = NU + ND;
   constexpr int NSPM = GENERAL ? PCG_MAX_NSP : 2;              // setpoints handled by this instantiation
   constexpr int NDOM = GENERAL ? PCG_MAX_ND : 1;
   constexpr int NTLM = GENERAL ? PCG_MAX_NTAIL : 1;
+  constexpr int NCONM = GENERAL ? PCG_MAX_NCON : 4;            // constraints handled by this instantiation
   const int64_t env0 = (static_cast<int64_t>(blockIdx.x) * kBlock + threadIdx.x) * EPT;
-  if (env0 >= n) return;
-  const bool vec = vec_i != 0;
-  bool ok[EPT];
-#pragma unroll
-  for (int e = 0; e < EPT; ++e) ok[e] = env0 + e < n;
+  if (env0 >= n) return;                                       // EPT == 2 implies even n: both envs valid
 
   const int flags = d.flags;
   const bool norm_a = flags & PCG_F_NORMALISE_A;
@@ -252,13 +246,14 @@ rollout_kernel(const __grid_constant__ pcg_desc d, const __grid_constant__ pcg_i
   const int nsp = d.nsp, n_con = d.n_con;
   const int nd_obs = GENERAL ? d.nd_obs : 0, n_tail = GENERAL ? d.n_tail : 0;
   const int n_obs = NX + nsp + nd_obs + n_tail;
+  const int noise = d.noise;
 
   // ---- carried state
   double x[EPT][NX];
 #pragma unroll
   for (int i = 0; i < NX; ++i) {
     double v[EPT];
-    ld_row<EPT>(io.x + i * n + env0, vec, ok, v);
+    ld_row<EPT>(io.x + i * n + env0, v);
 #pragma unroll
     for (int e = 0; e < EPT; ++e) x[e][i] = v[e];
   }
@@ -268,7 +263,7 @@ rollout_kernel(const __grid_constant__ pcg_desc d, const __grid_constant__ pcg_i
     double v[EPT];
 #pragma unroll
     for (int e = 0; e < EPT; ++e) v[e] = 0.0;
-    if (a_delta) ld_row<EPT>(io.a_save + j * n + env0, vec, ok, v);
+    if (a_delta) ld_row<EPT>(io.a_save + j * n + env0, v);
 #pragma unroll
     for (int e = 0; e < EPT; ++e) a_save[e][j] = v[e];
   }
@@ -278,7 +273,7 @@ rollout_kernel(const __grid_constant__ pcg_desc d, const __grid_constant__ pcg_i
     double v[EPT];
 #pragma unroll
     for (int e = 0; e < EPT; ++e) v[e] = 0.0;
-    if (GENERAL && j < n_tail) ld_row<EPT>(io.tail + j * n + env0, vec, ok, v);
+    if (GENERAL && j < n_tail) ld_row<EPT>(io.tail + j * n + env0, v);
 #pragma unroll
     for (int e = 0; e < EPT; ++e) tail[e][j] = v[e];
   }
@@ -288,10 +283,10 @@ rollout_kernel(const __grid_constant__ pcg_desc d, const __grid_constant__ pcg_i
   double h_carry[EPT];
 #pragma unroll
   for (int e = 0; e < EPT; ++e) {
-    done[e] = (io.done_state && ok[e]) ? (io.done_state[env0 + e] != 0) : false;
+    done[e] = io.done_state ? (io.done_state[env0 + e] != 0) : false;
     status[e] = 0;
     n_rhs[e] = 0;
-    h_carry[e] = (ADAPTIVE && io.h_carry && ok[e]) ? io.h_carry[env0 + e] : 0.0;
+    h_carry[e] = (ADAPTIVE && io.h_carry) ? io.h_carry[env0 + e] : 0.0;
   }
 
   // ---- per-thread stream pointers, advanced by a uniform stride every interval
@@ -304,24 +299,31 @@ rollout_kernel(const __grid_constant__ pcg_desc d, const __grid_constant__ pcg_i
   uint8_t* pd = io.done ? io.done + env0 : nullptr;
   uint8_t* pv = io.violated ? io.violated + env0 : nullptr;
 
-  // setpoints: SP[t] is shown in the observation, SP[t+1] enters the reward (pcgym.py:432-441, 555)
+  // setpoints: SP[t] is shown in the observation, SP[t+1] enters the reward (pcgym.py:432-441, 555).
+  // psp[j] walks the schedule one time index per interval; two values are carried in registers.
+  const double* psp[NSPM];
   double sp_cur[NSPM][EPT], sp_nxt[NSPM][EPT];
 #pragma unroll
-  for (int j = 0; j < NSPM; ++j)
+  for (int j = 0; j < NSPM; ++j) {
+    psp[j] = nullptr;
 #pragma unroll
-    for (int e = 0; e < EPT; ++e) {
-      sp_cur[j][e] = sp_nxt[j][e] = 0.0;
-      if (j < nsp) {
-        const double* b = io.sp + j * io.sp_sj + (ok[e] ? env0 + e : env0) * io.sp_se;
-        sp_cur[j][e] = b[static_cast<int64_t>(t0) * io.sp_st];
-        sp_nxt[j][e] = b[static_cast<int64_t>(t0 + 1) * io.sp_st];
+    for (int e = 0; e < EPT; ++e) sp_cur[j][e] = sp_nxt[j][e] = 0.0;
+    if (j < nsp) {
+      psp[j] = io.sp + j * io.sp_sj + env0 * io.sp_se + static_cast<int64_t>(t0) * io.sp_st;
+#pragma unroll
+      for (int e = 0; e < EPT; ++e) {
+        sp_cur[j][e] = psp[j][e * io.sp_se];
+        sp_nxt[j][e] = psp[j][e * io.sp_se + io.sp_st];
       }
+      psp[j] += 2 * io.sp_st;                                 // -> SP[t0 + 2]
     }
+  }
 
   // register double buffer for the streamed actions
   double a_nxt[NU][EPT];
 #pragma unroll
-  for (int j = 0; j < NU; ++j) ld_row<EPT>(pa + j * n, vec, ok, a_nxt[j]);
+  for (int j = 0; j < NU; ++j) ld_row<EPT>(pa + j * n, a_nxt[j]);
+  const uint2 key = make_uint2(static_cast<uint32_t>(d.seed), static_cast<uint32_t>(d.seed >> 32));
 
 #pragma unroll 1
   for (int k = 0; k < k_steps; ++k) {
@@ -335,17 +337,19 @@ rollout_kernel(const __grid_constant__ pcg_desc d, const __grid_constant__ pcg_i
     pa += static_cast<int64_t>(NU) * n;
     if (k + 1 < k_steps) {
 #pragma unroll
-      for (int j = 0; j < NU; ++j) ld_row<EPT>(pa + j * n, vec, ok, a_nxt[j]);
+      for (int j = 0; j < NU; ++j) ld_row<EPT>(pa + j * n, a_nxt[j]);
     }
     double sp_fut[NSPM][EPT];                                                  // SP[t+2], consumed next interval
 #pragma unroll
-    for (int j = 0; j < NSPM; ++j)
+    for (int j = 0; j < NSPM; ++j) {
 #pragma unroll
-      for (int e = 0; e < EPT; ++e) {
-        sp_fut[j][e] = sp_nxt[j][e];
-        if (j < nsp && t + 2 < d.N)
-          sp_fut[j][e] = io.sp[j * io.sp_sj + (ok[e] ? env0 + e : env0) * io.sp_se + static_cast<int64_t>(t + 2) * io.sp_st];
+      for (int e = 0; e < EPT; ++e) sp_fut[j][e] = sp_nxt[j][e];
+      if (j < nsp && t + 2 < d.N) {
+#pragma unroll
+        for (int e = 0; e < EPT; ++e) sp_fut[j][e] = psp[j][e * io.sp_se];
+        psp[j] += io.sp_st;
       }
+    }
 
     // ---- action -> physical input (pcgym.py:372-383)
     double uk[EPT][NUK];
@@ -367,7 +371,7 @@ rollout_kernel(const __grid_constant__ pcg_desc d, const __grid_constant__ pcg_i
       for (int i = 0; i < ND; ++i) {
         double v = d.d_default[i];
         if (dist_on && d.d_src[i] >= 0)
-          v = io.dist[static_cast<int64_t>(t + 1) * io.d_st + d.d_src[i] * io.d_sj + (ok[e] ? env0 + e : env0) * io.d_se];
+          v = io.dist[static_cast<int64_t>(t + 1) * io.d_st + d.d_src[i] * io.d_sj + (env0 + e) * io.d_se];
         uk[e][NU + i] = v;
       }
     }
@@ -384,39 +388,49 @@ rollout_kernel(const __grid_constant__ pcg_desc d, const __grid_constant__ pcg_i
         dslot[e][j] = v;
       }
 
-    // ---- constraint evaluator over state' = [x | sp | dslot | tail] and uk; g > 0 = violated
+    // ---- constraint evaluator over state' = [x | sp | dslot | tail] and uk; g > 0 = violated.
+    // Fully unrolled over the constraint index so G and h are direct constant-bank operands.
     auto constraints = [&](const double (&sps)[NSPM][EPT], double* gout, bool (&viol)[EPT]) {
 #pragma unroll
       for (int e = 0; e < EPT; ++e) viol[e] = false;
-#pragma unroll 1
-      for (int c = 0; c < n_con; ++c) {
-        const uint32_t mx = d.con_mask_x[c], mu = d.con_mask_u[c];
-        double g[EPT];
 #pragma unroll
-        for (int e = 0; e < EPT; ++e) {
-          double acc = d.con_h[c];
+      for (int c = 0; c < NCONM; ++c) {
+        if (c < n_con) {
+          const uint32_t mx = d.con_mask_x[c], mu = d.con_mask_u[c];
+          double g[EPT];
 #pragma unroll
-          for (int i = 0; i < NX; ++i)
-            if (mx >> i & 1u) acc = fma(d.con_gx[c][i], x[e][i], acc);
+          for (int e = 0; e < EPT; ++e) g[e] = d.con_h[c];
+#pragma unroll
+          for (int i = 0; i < NX; ++i) {
+            const bool on = mx >> i & 1u;
+#pragma unroll
+            for (int e = 0; e < EPT; ++e) g[e] = on ? fma(d.con_gx[c][i], x[e][i], g[e]) : g[e];
+          }
           if (GENERAL && (mx >> NX)) {               // rare: constraint reads SP / disturbance / tail slots
 #pragma unroll
-            for (int j = 0; j < NSPM; ++j)
-              if (j < nsp && (mx >> (NX + j) & 1u)) acc = fma(d.con_gx[c][NX + j], sps[j][e], acc);
+            for (int e = 0; e < EPT; ++e) {
 #pragma unroll
-            for (int j = 0; j < NDOM; ++j)
-              if (j < nd_obs && (mx >> (NX + nsp + j) & 1u)) acc = fma(d.con_gx[c][NX + nsp + j], dslot[e][j], acc);
+              for (int j = 0; j < NSPM; ++j)
+                if (j < nsp && (mx >> (NX + j) & 1u)) g[e] = fma(d.con_gx[c][NX + j], sps[j][e], g[e]);
 #pragma unroll
-            for (int j = 0; j < NTLM; ++j)
-              if (j < n_tail && (mx >> (NX + nsp + nd_obs + j) & 1u))
-                acc = fma(d.con_gx[c][NX + nsp + nd_obs + j], tail[e][j], acc);
+              for (int j = 0; j < NDOM; ++j)
+                if (j < nd_obs && (mx >> (NX + nsp + j) & 1u)) g[e] = fma(d.con_gx[c][NX + nsp + j], dslot[e][j], g[e]);
+#pragma unroll
+              for (int j = 0; j < NTLM; ++j)
+                if (j < n_tail && (mx >> (NX + nsp + nd_obs + j) & 1u))
+                  g[e] = fma(d.con_gx[c][NX + nsp + nd_obs + j], tail[e][j], g[e]);
+            }
           }
 #pragma unroll
-          for (int i = 0; i < NUK; ++i)
-            if (mu >> i & 1u) acc = fma(d.con_gu[c][i], uk[e][i], acc);
-          g[e] = acc;
-          viol[e] = viol[e] || (acc > 0.0);           // NaN compares false, as np.any(g > 0)
+          for (int i = 0; i < NUK; ++i) {
+            const bool on = mu >> i & 1u;
+#pragma unroll
+            for (int e = 0; e < EPT; ++e) g[e] = on ? fma(d.con_gu[c][i], uk[e][i], g[e]) : g[e];
+          }
+#pragma unroll
+          for (int e = 0; e < EPT; ++e) viol[e] = viol[e] || (g[e] > 0.0);   // NaN compares false, as np.any(g > 0)
+          if (gout) st_row<EPT>(gout + c * n, g);
         }
-        if (gout) st_row<EPT>(gout + c * n, vec, ok, g);
       }
     };
 
@@ -434,13 +448,71 @@ rollout_kernel(const __grid_constant__ pcg_desc d, const __grid_constant__ pcg_i
         if (v0[e] && done_on_v) done[e] = true;
     }
 
+    // ---- Gaussian draws for this interval.  They depend on (seed, env, t) only, so they are issued in the
+    // same basic block as the integrator stages: independent work that fills the FP64 dependency stalls.
+    double z[EPT][NX];
+    auto draw = [&]() {
+#pragma unroll
+      for (int e = 0; e < EPT; ++e)
+#pragma unroll
+        for (int i = 0; i < NX; ++i) z[e][i] = 0.0;
+      if (noise == PCG_NOISE_PHILOX) {
+#pragma unroll
+        for (int e = 0; e < EPT; ++e) {
+          const uint64_t gid = static_cast<uint64_t>(d.env_id0 + env0 + e);
+#pragma unroll
+          for (int i = 0; i < NX; i += 2) {
+            double z0, z1;
+            normal_pair_f64(philox4x32_10(make_uint4(static_cast<uint32_t>(gid), static_cast<uint32_t>(gid >> 32),
+                                                     static_cast<uint32_t>(t_new), i / 2), key), z0, z1);
+            z[e][i] = z0;
+            if (i + 1 < NX) z[e][i + 1] = z1;
+          }
+        }
+      } else if (noise == PCG_NOISE_PHILOX_F32) {
+#pragma unroll
+        for (int e = 0; e < EPT; ++e) {
+          const uint64_t gid = static_cast<uint64_t>(d.env_id0 + env0 + e);
+#pragma unroll
+          for (int i = 0; i < NX; i += 4) {
+            double zq[4];
+            normal_quad_f32(philox4x32_10(make_uint4(static_cast<uint32_t>(gid), static_cast<uint32_t>(gid >> 32),
+                                                     static_cast<uint32_t>(t_new), i / 4), key), zq);
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              if (i + q < NX) z[e][i + q] = zq[q];
+          }
+        }
+      } else if (noise == PCG_NOISE_EXTERNAL) {
+#pragma unroll
+        for (int i = 0; i < NX; ++i)
+          if (d.noise_pct[i] != 0.0) {
+            double v[EPT];
+            ld_row<EPT>(pz + i * n, v);
+#pragma unroll
+            for (int e = 0; e < EPT; ++e) z[e][i] = v[e];
+          }
+      }
+    };
+
     // ---- integrate over the control interval, input held (integrator.py:90-107)
     if constexpr (ADAPTIVE && TB::EMBEDDED) {
+      draw();
 #pragma unroll
       for (int e = 0; e < EPT; ++e)
         advance_adaptive<M, TB>(dv, x[e], uk[e], d.dt, d.rtol, d.atol, d.max_steps, h_carry[e], n_rhs[e], status[e]);
     } else {
-      advance_fixed<M, TB, EPT>(dv, x, uk, d.n_sub);
+      typename M::Aux aux[EPT];
+#pragma unroll
+      for (int e = 0; e < EPT; ++e) M::prep(dv.p, uk[e], aux[e]);
+      if (d.n_sub == 1) {
+        draw();
+        rk_step_fixed<M, TB, EPT>(dv, aux, x, uk);
+      } else {
+        draw();
+#pragma unroll 1
+        for (int s = 0; s < d.n_sub; ++s) rk_step_fixed<M, TB, EPT>(dv, aux, x, uk);
+      }
     }
 
     // ---- constraints on the new state (pcgym.py:444-446), done (pcgym.py:448-449)
@@ -484,52 +556,6 @@ rollout_kernel(const __grid_constant__ pcg_desc d, const __grid_constant__ pcg_i
       }
     }
 
-    // ---- measurement noise on the model states only (pcgym.py:453-466)
-    double ox[EPT][NX];
-#pragma unroll
-    for (int e = 0; e < EPT; ++e)
-#pragma unroll
-      for (int i = 0; i < NX; ++i) ox[e][i] = x[e][i];
-    if (d.noise == PCG_NOISE_PHILOX) {
-      const uint2 key = make_uint2(static_cast<uint32_t>(d.seed), static_cast<uint32_t>(d.seed >> 32));
-#pragma unroll
-      for (int e = 0; e < EPT; ++e) {
-        const uint64_t gid = static_cast<uint64_t>(d.env_id0 + env0 + e);
-#pragma unroll
-        for (int i = 0; i < NX; i += 2) {
-          double z0, z1;
-          normal_pair_f64(philox4x32_10(make_uint4(static_cast<uint32_t>(gid), static_cast<uint32_t>(gid >> 32),
-                                                   static_cast<uint32_t>(t_new), i / 2), key), z0, z1);
-          ox[e][i] = fma(z0 * x[e][i], d.noise_pct[i], x[e][i]);
-          if (i + 1 < NX) ox[e][i + 1] = fma(z1 * x[e][i + 1], d.noise_pct[i + 1], x[e][i + 1]);
-        }
-      }
-    } else if (d.noise == PCG_NOISE_PHILOX_F32) {
-      const uint2 key = make_uint2(static_cast<uint32_t>(d.seed), static_cast<uint32_t>(d.seed >> 32));
-#pragma unroll
-      for (int e = 0; e < EPT; ++e) {
-        const uint64_t gid = static_cast<uint64_t>(d.env_id0 + env0 + e);
-#pragma unroll
-        for (int i = 0; i < NX; i += 4) {
-          double z[4];
-          normal_quad_f32(philox4x32_10(make_uint4(static_cast<uint32_t>(gid), static_cast<uint32_t>(gid >> 32),
-                                                   static_cast<uint32_t>(t_new), i / 4), key), z);
-#pragma unroll
-          for (int q = 0; q < 4; ++q)
-            if (i + q < NX) ox[e][i + q] = fma(z[q] * x[e][i + q], d.noise_pct[i + q], x[e][i + q]);
-        }
-      }
-    } else if (d.noise == PCG_NOISE_EXTERNAL) {
-#pragma unroll
-      for (int i = 0; i < NX; ++i)
-        if (d.noise_pct[i] != 0.0) {
-          double z[EPT];
-          ld_row<EPT>(pz + i * n, vec, ok, z);
-#pragma unroll
-          for (int e = 0; e < EPT; ++e) ox[e][i] = fma(z[e] * x[e][i], d.noise_pct[i], x[e][i]);
-        }
-    }
-
     // ---- outputs (evict-first: never re-read by this kernel)
     if (px) {
 #pragma unroll
@@ -537,8 +563,9 @@ rollout_kernel(const __grid_constant__ pcg_desc d, const __grid_constant__ pcg_i
         double v[EPT];
 #pragma unroll
         for (int e = 0; e < EPT; ++e) v[e] = x[e][i];
-        st_row<EPT>(px + i * n, vec, ok, v);
+        st_row<EPT>(px + i * n, v);
       }
+      px += static_cast<int64_t>(NX) * n;
     }
     if (po) {
       const uint32_t zmask = d.obs_zero_mask;
@@ -547,10 +574,12 @@ rollout_kernel(const __grid_constant__ pcg_desc d, const __grid_constant__ pcg_i
         double v[EPT];
 #pragma unroll
         for (int e = 0; e < EPT; ++e) {
-          v[e] = norm_o ? fma(ox[e][i], d.o_scale[i], d.o_off[i]) : ox[e][i];  // pcgym.py:483-493
+          // measurement noise on the model states only: obs = x + z x pct (pcgym.py:453-466)
+          const double ox = fma(z[e][i] * x[e][i], d.noise_pct[i], x[e][i]);
+          v[e] = norm_o ? fma(ox, d.o_scale[i], d.o_off[i]) : ox;             // pcgym.py:483-493
           if (zmask >> i & 1u) v[e] = 0.0;                                     // pcgym.py:495-498
         }
-        st_row<EPT>(po + i * n, vec, ok, v);
+        st_row<EPT>(po + i * n, v);
       }
 #pragma unroll
       for (int j = 0; j < NSPM; ++j)
@@ -559,7 +588,7 @@ rollout_kernel(const __grid_constant__ pcg_desc d, const __grid_constant__ pcg_i
           double v[EPT];
 #pragma unroll
           for (int e = 0; e < EPT; ++e) v[e] = norm_o ? fma(sp_cur[j][e], d.o_scale[i], d.o_off[i]) : sp_cur[j][e];
-          st_row<EPT>(po + i * n, vec, ok, v);
+          st_row<EPT>(po + i * n, v);
         }
       if (GENERAL) {
 #pragma unroll
@@ -569,7 +598,7 @@ rollout_kernel(const __grid_constant__ pcg_desc d, const __grid_constant__ pcg_i
             double v[EPT];
 #pragma unroll
             for (int e = 0; e < EPT; ++e) v[e] = norm_o ? fma(dslot[e][j], d.o_scale[i], d.o_off[i]) : dslot[e][j];
-            st_row<EPT>(po + i * n, vec, ok, v);
+            st_row<EPT>(po + i * n, v);
           }
 #pragma unroll
         for (int j = 0; j < NTLM; ++j)
@@ -578,22 +607,16 @@ rollout_kernel(const __grid_constant__ pcg_desc d, const __grid_constant__ pcg_i
             double v[EPT];
 #pragma unroll
             for (int e = 0; e < EPT; ++e) v[e] = norm_o ? fma(tail[e][j], d.o_scale[i], d.o_off[i]) : tail[e][j];
-            st_row<EPT>(po + i * n, vec, ok, v);
+            st_row<EPT>(po + i * n, v);
           }
       }
+      po += static_cast<int64_t>(n_obs) * n;
     }
-    if (pr) st_row<EPT>(pr, vec, ok, r);
-    if (pd) st_flags<EPT>(pd, vec, ok, done);
-    if (pv) st_flags<EPT>(pv, vec, ok, violated);
-
-    // ---- advance the streams
-    if (pz) pz += static_cast<int64_t>(NX) * n;
-    if (px) px += static_cast<int64_t>(NX) * n;
-    if (po) po += static_cast<int64_t>(n_obs) * n;
-    if (pr) pr += n;
+    if (pr) { st_row<EPT>(pr, r); pr += n; }
+    if (pd) { st_flags<EPT>(pd, done); pd += n; }
+    if (pv) { st_flags<EPT>(pv, violated); pv += n; }
     if (pg) pg += static_cast<int64_t>(n_con) * n;
-    if (pd) pd += n;
-    if (pv) pv += n;
+    if (pz) pz += static_cast<int64_t>(NX) * n;
 #pragma unroll
     for (int j = 0; j < NSPM; ++j)
 #pragma unroll
@@ -612,7 +635,7 @@ rollout_kernel(const __grid_constant__ pcg_desc d, const __grid_constant__ pcg_i
       v[e] = x[e][i];
       if (!isfinite(v[e])) status[e] |= PCG_ST_NONFINITE;
     }
-    st_row<EPT>(io.x + i * n + env0, vec, ok, v);
+    st_row<EPT>(io.x + i * n + env0, v);
   }
   if (a_delta) {
 #pragma unroll
@@ -620,12 +643,11 @@ rollout_kernel(const __grid_constant__ pcg_desc d, const __grid_constant__ pcg_i
       double v[EPT];
 #pragma unroll
       for (int e = 0; e < EPT; ++e) v[e] = a_save[e][j];
-      st_row<EPT>(io.a_save + j * n + env0, vec, ok, v);
+      st_row<EPT>(io.a_save + j * n + env0, v);
     }
   }
 #pragma unroll
   for (int e = 0; e < EPT; ++e) {
-    if (!ok[e]) continue;
     if (io.done_state) io.done_state[env0 + e] = done[e] ? 1 : 0;
     if (io.status && status[e]) io.status[env0 + e] |= static_cast<uint8_t>(status[e]);
     if (ADAPTIVE && io.h_carry) io.h_carry[env0 + e] = h_carry[e];
