@@ -5,7 +5,7 @@
 
 #include <cstdlib>
 
-#include "rollout_kernel.cuh"
+#include "rollout_fast.cuh"
 
 namespace pcg {
 
@@ -47,11 +47,52 @@ inline int ept_override() {
   return v;
 }
 
+// the straight-line, software-pipelined kernel covers: fixed step with n_sub == 1, lean observation vector,
+// SP reward with <= 2 setpoints, <= 2 constraints, no a_delta, Philox / no noise, all trajectory outputs wanted
+template <class M>
+inline bool fast_ok(const pcg_desc& d, const pcg_io& io) {
+  if ((d.flags & PCG_F_ADAPTIVE) || d.n_sub != 1 || needs_general<M>(d)) return false;
+  if ((d.flags & PCG_F_A_DELTA) && (d.flags & PCG_F_NORMALISE_A)) return false;
+  if (d.reward != PCG_REWARD_SP || d.nsp < 1 || d.nsp > kFastNsp || d.n_con > kFastNcon) return false;
+  if (d.noise == PCG_NOISE_EXTERNAL) return false;
+  if (!io.x_traj || !io.obs || !io.reward || !io.done || !io.violated) return false;
+  if (d.n_con > 0 && !io.g) return false;
+  static const bool off = std::getenv("PCG_NO_FAST") != nullptr;               // profiling knob
+  return !off;
+}
+
+template <class M, class TB, int EPT>
+cudaError_t launch_fast(const pcg_desc& d, const pcg_io& io, int64_t n_env, int t0, int k_steps, cudaStream_t s) {
+  const int64_t threads = (n_env + EPT - 1) / EPT;
+  const unsigned grid = static_cast<unsigned>((threads + kBlock - 1) / kBlock);
+  const Derived<M, TB> dv = make_derived<M, TB>(d);
+  switch (d.noise) {
+    case PCG_NOISE_OFF:
+      fast_rollout_kernel<M, TB, PCG_NOISE_OFF, EPT><<<grid, kBlock, 0, s>>>(d, io, dv, n_env, t0, k_steps);
+      break;
+    case PCG_NOISE_PHILOX:
+      fast_rollout_kernel<M, TB, PCG_NOISE_PHILOX, EPT><<<grid, kBlock, 0, s>>>(d, io, dv, n_env, t0, k_steps);
+      break;
+    default:
+      fast_rollout_kernel<M, TB, PCG_NOISE_PHILOX_F32, EPT><<<grid, kBlock, 0, s>>>(d, io, dv, n_env, t0, k_steps);
+      break;
+  }
+  return cudaGetLastError();
+}
+
 template <class M, class TB, bool ADAPTIVE, bool GENERAL>
 cudaError_t launch_e(const pcg_desc& d, const pcg_io& io, int64_t n_env, int t0, int k_steps, cudaStream_t s) {
+  const bool two = M::EPT == 2 && ept_override() != 1 && vector_ok(io, n_env);
+  if constexpr (!ADAPTIVE && !GENERAL) {
+    if (fast_ok<M>(d, io)) {
+      if constexpr (M::EPT == 2) {
+        if (two) return launch_fast<M, TB, 2>(d, io, n_env, t0, k_steps, s);
+      }
+      return launch_fast<M, TB, 1>(d, io, n_env, t0, k_steps, s);
+    }
+  }
   if constexpr (!ADAPTIVE && M::EPT == 2) {
-    if (ept_override() != 1 && vector_ok(io, n_env))
-      return launch_one<M, TB, ADAPTIVE, GENERAL, 2>(d, io, n_env, t0, k_steps, s);
+    if (two) return launch_one<M, TB, ADAPTIVE, GENERAL, 2>(d, io, n_env, t0, k_steps, s);
   }
   return launch_one<M, TB, ADAPTIVE, GENERAL, 1>(d, io, n_env, t0, k_steps, s);
 }

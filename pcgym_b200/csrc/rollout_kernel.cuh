@@ -225,7 +225,7 @@ PCG_DEV void advance_adaptive(const Derived<M, TB>& dv, double (&x)[M::NX], cons
 
 // ------------------------------------------------------------------ the kernel
 template <class M, class TB, bool ADAPTIVE, bool GENERAL, int EPT>
-__global__ void __launch_bounds__(kBlock, M::MIN_BLOCKS)
+__global__ void __launch_bounds__(kBlock, (EPT == 1 && !ADAPTIVE) ? M::MIN_BLOCKS_EPT1 : M::MIN_BLOCKS)
 rollout_kernel(const __grid_constant__ pcg_desc d, const __grid_constant__ pcg_io io,
                const __grid_constant__ Derived<M, TB> dv, const int64_t n, const int t0, const int k_steps) {
   constexpr int NX = M::NX, NU = M::NU, ND = M::ND, NUK = NU + ND;
@@ -396,36 +396,36 @@ rollout_kernel(const __grid_constant__ pcg_desc d, const __grid_constant__ pcg_i
 #pragma unroll
       for (int c = 0; c < NCONM; ++c) {
         if (c < n_con) {
-          const uint32_t mx = d.con_mask_x[c], mu = d.con_mask_u[c];
           double g[EPT];
 #pragma unroll
           for (int e = 0; e < EPT; ++e) g[e] = d.con_h[c];
+          // dense over the model states and inputs (zero coefficients cost one DFMA but no predicate
+          // logic); the optional observation slots are sparse and stay masked
 #pragma unroll
-          for (int i = 0; i < NX; ++i) {
-            const bool on = mx >> i & 1u;
+          for (int i = 0; i < NX; ++i)
 #pragma unroll
-            for (int e = 0; e < EPT; ++e) g[e] = on ? fma(d.con_gx[c][i], x[e][i], g[e]) : g[e];
-          }
-          if (GENERAL && (mx >> NX)) {               // rare: constraint reads SP / disturbance / tail slots
+            for (int e = 0; e < EPT; ++e) g[e] = fma(d.con_gx[c][i], x[e][i], g[e]);
 #pragma unroll
-            for (int e = 0; e < EPT; ++e) {
+          for (int i = 0; i < NUK; ++i)
 #pragma unroll
-              for (int j = 0; j < NSPM; ++j)
-                if (j < nsp && (mx >> (NX + j) & 1u)) g[e] = fma(d.con_gx[c][NX + j], sps[j][e], g[e]);
+            for (int e = 0; e < EPT; ++e) g[e] = fma(d.con_gu[c][i], uk[e][i], g[e]);
+          if constexpr (GENERAL) {
+            const uint32_t mx = d.con_mask_x[c];
+            if (mx >> NX) {                           // rare: constraint reads SP / disturbance / tail slots
 #pragma unroll
-              for (int j = 0; j < NDOM; ++j)
-                if (j < nd_obs && (mx >> (NX + nsp + j) & 1u)) g[e] = fma(d.con_gx[c][NX + nsp + j], dslot[e][j], g[e]);
+              for (int e = 0; e < EPT; ++e) {
 #pragma unroll
-              for (int j = 0; j < NTLM; ++j)
-                if (j < n_tail && (mx >> (NX + nsp + nd_obs + j) & 1u))
-                  g[e] = fma(d.con_gx[c][NX + nsp + nd_obs + j], tail[e][j], g[e]);
+                for (int j = 0; j < NSPM; ++j)
+                  if (j < nsp && (mx >> (NX + j) & 1u)) g[e] = fma(d.con_gx[c][NX + j], sps[j][e], g[e]);
+#pragma unroll
+                for (int j = 0; j < NDOM; ++j)
+                  if (j < nd_obs && (mx >> (NX + nsp + j) & 1u)) g[e] = fma(d.con_gx[c][NX + nsp + j], dslot[e][j], g[e]);
+#pragma unroll
+                for (int j = 0; j < NTLM; ++j)
+                  if (j < n_tail && (mx >> (NX + nsp + nd_obs + j) & 1u))
+                    g[e] = fma(d.con_gx[c][NX + nsp + nd_obs + j], tail[e][j], g[e]);
+              }
             }
-          }
-#pragma unroll
-          for (int i = 0; i < NUK; ++i) {
-            const bool on = mu >> i & 1u;
-#pragma unroll
-            for (int e = 0; e < EPT; ++e) g[e] = on ? fma(d.con_gu[c][i], uk[e][i], g[e]) : g[e];
           }
 #pragma unroll
           for (int e = 0; e < EPT; ++e) viol[e] = viol[e] || (g[e] > 0.0);   // NaN compares false, as np.any(g > 0)
