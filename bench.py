@@ -40,6 +40,7 @@ K_STEPS = N_HORIZON - 1
 # SURVEY 8(d) quotes 82 B because it assumes per-env setpoint tensors (8 B more read per env-step); the
 # headline uses the reference's shared setpoint schedule, which costs no per-env traffic.
 BYTES_PER_ENV_STEP = 74
+NCU_DRAM_BYTES_PER_LAUNCH = 53387520 + 372079872      # profiles/r1_cstr_v5_ncu_summary.txt
 HEADLINE_INTEGRATOR = {"scheme": "tsit5", "adaptive": False, "n_sub": 1}
 
 
@@ -161,7 +162,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--n-envs", type=int, default=N_ENVS, help="envs per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--ref-envs-per-worker", type=int, default=8)
+    ap.add_argument("--ref-envs-per-worker", type=int, default=48)
     ap.add_argument("--noise-mode", default="philox", choices=["philox", "philox_f32", "off"],
                     help="experiment knob; the headline is 'philox' (fp64 Box-Muller)")
     args = ap.parse_args()
@@ -176,7 +177,7 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle import baseline
-        cpu = baseline.run(envs_per_worker=12)
+        cpu = baseline.run(envs_per_worker=300)          # ~6 s of CPU work per core
         cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
 
     import torch
@@ -303,8 +304,13 @@ def main():
                    "l2": "inputs+outputs per launch ~0.48 GB > 126 MB L2; action buffers rotate over a ring of 3",
                    "parallelism": f"env-sharded x{world}, no collective"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "peak_source": peak_src, "bytes_per_env_step": BYTES_PER_ENV_STEP,
-                     "kernel_ms": kern_ms_max, "kernel": "pcg::rollout_kernel<Cstr,Tsit5,false>"},
+                     "traffic": NCU_DRAM_BYTES_PER_LAUNCH if n == N_ENVS else None,
+                     "traffic_note": "dram__bytes_read+write.sum of one launch, profiles/r1_cstr_v5_ncu_summary.txt "
+                                     "(~55 MB of the stores are still in L2 at kernel end)",
+                     "algorithmic_bytes": BYTES_PER_ENV_STEP * env_steps_per_launch,
+                     "peak_source": peak_src, "bytes_per_env_step": BYTES_PER_ENV_STEP,
+                     "kernel_ms": kern_ms_max, "kernel": "pcg::fast_rollout_kernel<Cstr,Tsit5,PHILOX,2>",
+                     "fp64_note": "FP64-pipe/latency bound, not HBM bound: see profiles/README.md"},
         "cpu_baseline": cpu,
         "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": Ke, "ms_per_step": e2e_ms / Ke},
