@@ -70,7 +70,10 @@ enum pcg_noise {
 enum pcg_reward {
   PCG_REWARD_NONE = 0,   /* custom reward handled by the caller              */
   PCG_REWARD_SP = 1,     /* SP_reward_fn    pcgym.py:535-558                 */
-  PCG_REWARD_BATCH = 2   /* batch_reward_fn pcgym.py:502-532                 */
+  PCG_REWARD_BATCH = 2,  /* batch_reward_fn pcgym.py:502-532                 */
+  PCG_REWARD_OCP = 3     /* the paper scripts' custom reward, fused: normalised squared setpoint error
+                            on the NOISY observation + R * (delta u_norm)^2
+                            (pc-gym_paper/train_policies/cstr/custom_reward.py:3-39)          */
 };
 
 enum pcg_flags {
@@ -157,6 +160,12 @@ typedef struct pcg_desc {
   double con_h[PCG_MAX_NCON];
   uint32_t con_mask_x[PCG_MAX_NCON];  /* nonzero columns of con_gx */
   uint32_t con_mask_u[PCG_MAX_NCON];  /* nonzero columns of con_gu */
+
+  /* PCG_REWARD_OCP */
+  double ocp_R;                    /* control-cost weight R */
+  double ocp_inv_span[PCG_MAX_NSP];/* 1/(o_hi - o_lo) of each setpoint's state */
+  int32_t ocp_mode;                /* 0: R*u_norm^2   1: R*(u_norm - u_prev_norm)^2   2: as 1, io.u_prev not yet valid */
+  int32_t _pad3;
 } pcg_desc;
 
 /* Device buffers.  n = n_env, K = k_steps of this call.  Any output pointer may be NULL (not written). */
@@ -182,6 +191,7 @@ typedef struct pcg_io {
   uint8_t* status;         /* in/out [n] OR-accumulated PCG_ST_* bits, or NULL                 */
   double* h_carry;         /* in/out [n] adaptive step size carried between intervals, or NULL */
   int32_t* n_rhs;          /* in/out [n] accumulated RHS evaluations, or NULL                  */
+  double* u_prev;          /* in/out [nu_a][n] previous physical action (PCG_REWARD_OCP), or NULL */
 } pcg_io;
 
 /* ABI version of the loaded library. */

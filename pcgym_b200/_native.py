@@ -25,7 +25,7 @@ MODEL_IDS = {
 }
 SCHEMES = {"rk4": 0, "dopri5": 1, "rk45": 1, "tsit5": 2}
 NOISE = {"off": 0, "philox": 1, "external": 2, "philox_f32": 3}
-REWARD = {"none": 0, "sp": 1, "batch": 2}
+REWARD = {"none": 0, "sp": 1, "batch": 2, "ocp": 3}
 
 F_NORMALISE_A, F_NORMALISE_O, F_A_DELTA, F_R_PENALTY, F_DONE_ON_VIOLATION, F_ADAPTIVE = (1 << i for i in range(6))
 ST_NONFINITE, ST_STEPCAP = 1, 2
@@ -59,6 +59,7 @@ class Desc(C.Structure):
         ("con_h", f64 * MAX_NCON),
         ("con_mask_x", u32 * MAX_NCON),
         ("con_mask_u", u32 * MAX_NCON),
+        ("ocp_R", f64), ("ocp_inv_span", f64 * MAX_NSP), ("ocp_mode", i32), ("_pad3", i32),
     ]
 
 
@@ -72,6 +73,7 @@ class IO(C.Structure):
         ("x_traj", C.c_void_p), ("obs", C.c_void_p), ("reward", C.c_void_p),
         ("done", C.c_void_p), ("violated", C.c_void_p), ("g", C.c_void_p), ("g0", C.c_void_p),
         ("done_state", C.c_void_p), ("status", C.c_void_p), ("h_carry", C.c_void_p), ("n_rhs", C.c_void_p),
+        ("u_prev", C.c_void_p),
     ]
 
 

@@ -16,7 +16,7 @@ inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) 
 // 128-bit row access needs an even env count (every row then starts 16-byte aligned) and aligned bases
 inline bool vector_ok(const pcg_io& io, int64_t n) {
   if (n % 2) return false;
-  const void* f64[] = {io.x, io.a, io.a_save, io.z, io.tail, io.x_traj, io.obs, io.reward, io.g, io.g0};
+  const void* f64[] = {io.x, io.a, io.a_save, io.z, io.tail, io.x_traj, io.obs, io.reward, io.g, io.g0, io.u_prev};
   for (const void* p : f64)
     if (!al16(p)) return false;
   return (reinterpret_cast<uintptr_t>(io.done) & 1u) == 0 && (reinterpret_cast<uintptr_t>(io.violated) & 1u) == 0;

@@ -289,6 +289,19 @@ rollout_kernel(const __grid_constant__ pcg_desc d, const __grid_constant__ pcg_i
     h_carry[e] = (ADAPTIVE && io.h_carry) ? io.h_carry[env0 + e] : 0.0;
   }
 
+  const bool ocp = d.reward == PCG_REWARD_OCP;
+  double u_prev[EPT][NU];
+#pragma unroll
+  for (int j = 0; j < NU; ++j) {
+    double v[EPT];
+#pragma unroll
+    for (int e = 0; e < EPT; ++e) v[e] = 0.0;
+    if (ocp && io.u_prev) ld_row<EPT>(io.u_prev + j * n + env0, v);
+#pragma unroll
+    for (int e = 0; e < EPT; ++e) u_prev[e][j] = v[e];
+  }
+  bool u_prev_valid = d.ocp_mode != 2;
+
   // ---- per-thread stream pointers, advanced by a uniform stride every interval
   const double* pa = io.a + env0;
   const double* pz = io.z ? io.z + env0 : nullptr;
@@ -545,6 +558,37 @@ rollout_kernel(const __grid_constant__ pcg_desc d, const __grid_constant__ pcg_i
             if (penal && violated[e]) r[e] -= d.penalty;                       // once per SP key
           }
         }
+    } else if (ocp) {
+      // fused "OCP tracking" custom reward of the paper scripts (custom_reward.py:3-39): evaluated on the
+      // NOISY physical observation, setpoint SP[t+1], control cost on the normalised physical input
+#pragma unroll
+      for (int e = 0; e < EPT; ++e) {
+        double cost = 0.0;
+#pragma unroll
+        for (int j = 0; j < NSPM; ++j)
+          if (j < nsp) {
+            const int si = d.sp_state[j];
+            double xo = 0.0;
+#pragma unroll
+            for (int i = 0; i < NX; ++i) {
+              const double ox = fma(z[e][i] * x[e][i], d.noise_pct[i], x[e][i]);
+              xo = (si == i) ? ox : xo;
+            }
+            const double en = (xo - sp_nxt[j][e]) * d.ocp_inv_span[j];
+            cost = fma(en * en, d.r_scale[j], cost);
+          }
+#pragma unroll
+        for (int j = 0; j < NU; ++j) {
+          const double inv = 0.5 / d.a_scale[j];                               // 1 / (a_hi - a_lo)
+          const double un = (uk[e][j] - (d.a_off[j] - d.a_scale[j])) * inv;
+          const double up = ((u_prev_valid ? u_prev[e][j] : uk[e][j]) - (d.a_off[j] - d.a_scale[j])) * inv;
+          const double du = d.ocp_mode == 0 ? un : un - up;
+          cost = fma(d.ocp_R * du, du, cost);
+          u_prev[e][j] = uk[e][j];
+        }
+        r[e] = -cost;
+      }
+      u_prev_valid = true;
     } else if (d.reward == PCG_REWARD_BATCH) {                                 // pcgym.py:502-532
       if (t_new == d.N - 1) {
 #pragma unroll
@@ -644,6 +688,15 @@ rollout_kernel(const __grid_constant__ pcg_desc d, const __grid_constant__ pcg_i
 #pragma unroll
       for (int e = 0; e < EPT; ++e) v[e] = a_save[e][j];
       st_row<EPT>(io.a_save + j * n + env0, v);
+    }
+  }
+  if (ocp && io.u_prev) {
+#pragma unroll
+    for (int j = 0; j < NU; ++j) {
+      double v[EPT];
+#pragma unroll
+      for (int e = 0; e < EPT; ++e) v[e] = u_prev[e][j];
+      st_row<EPT>(io.u_prev + j * n + env0, v);
     }
   }
 #pragma unroll

@@ -74,9 +74,22 @@ class make_env:
         self.maximise_reward = True
         self.SP = P.get("SP")
         self.custom_reward = P.get("custom_reward") is not None
+        self._ocp = None
         if self.custom_reward:
             self.custom_reward_f = P["custom_reward"]
             self.reward = None
+            if isinstance(self.custom_reward_f, dict):
+                # declarative form of the paper scripts' reward: fused into the kernel (PCG_REWARD_OCP)
+                spec = dict(self.custom_reward_f)
+                if spec.pop("kind", "ocp_tracking") != "ocp_tracking":
+                    raise ValueError("custom_reward dict: only kind='ocp_tracking' is known")
+                self._ocp = {"R": float(spec.pop("R", 0.1)), "delta_u": bool(spec.pop("delta_u", True))}
+                if spec:
+                    raise ValueError(f"custom_reward dict: unknown keys {sorted(spec)}")
+                if self.SP is None:
+                    raise ValueError("custom_reward kind='ocp_tracking' needs SP")
+            elif not callable(self.custom_reward_f):
+                raise ValueError("custom_reward must be a callable or an 'ocp_tracking' dict")
         elif self.SP is not None:
             self.reward = "SP_reward_fn"
         else:
@@ -195,6 +208,8 @@ class make_env:
         in the kernel, so it is probed: g(0), g(e_i) give h and the columns of G, and random points verify
         that g really is affine in (state, uk).  Every constraint in the reference's docs and tests is."""
         nx, nu = self._n_obs, self.Nu
+        if isinstance(self.constraints, dict):
+            return self._box_constraints()
         g = lambda s, u: np.asarray(self.constraints(s, u), dtype=np.float64).reshape(-1)
         h = g(np.zeros(nx), np.zeros(nu))
         G = np.zeros((h.shape[0], nx + nu))
@@ -217,6 +232,36 @@ class make_env:
                     "constraints(x, u) is not affine in (x, u): only affine constraints can be fused "
                     "into the B200 step kernel")
         return G, h
+
+    def _box_constraints(self):
+        """Declarative bounds, the API of the reference's oracle / paper scripts
+        (`constraints={'T': [327, 321]}, cons_type={'T': ['<=', '>=']}`, oracle.py:127-134,
+        pc-gym_paper/constraint_showcase/constraint_paper.py:33-35).  Physical units; one row per bound."""
+        names = self.model.info()["states"]
+        inputs = self.model.info()["inputs"]
+        ctype = self.env_params.get("cons_type")
+        if ctype is None:
+            raise KeyError("cons_type")
+        rows, hs = [], []
+        for k, bounds in self.constraints.items():
+            for b, op in zip(np.atleast_1d(bounds), ctype[k]):
+                row = np.zeros(self._n_obs + self.Nu)
+                if k in names:
+                    col = names.index(k)
+                elif k in inputs:
+                    col = self._n_obs + inputs.index(k)
+                else:
+                    raise ValueError(f"'{k}' is not in list")
+                if op == "<=":
+                    row[col], h = 1.0, -float(b)            # x - b <= 0
+                elif op == ">=":
+                    row[col], h = -1.0, float(b)            # b - x <= 0
+                else:
+                    raise ValueError(f"cons_type entries must be '<=' or '>=', got {op!r}")
+                rows.append(row)
+                hs.append(h)
+        self.env_params.setdefault("constraint_units", "physical")
+        return np.array(rows), np.array(hs)
 
     # ------------------------------------------------------------------ host tables (setpoints, disturbances, x0)
     def _per_time(self, v, what):
@@ -283,7 +328,8 @@ class make_env:
         d.scheme = nat.SCHEMES[self.integrator["scheme"]]
         flags = 0
         flags |= nat.F_NORMALISE_A if self.normalise_a is True else 0
-        flags |= nat.F_NORMALISE_O if self.normalise_o is True else 0
+        self._host_reward = self.custom_reward and self._ocp is None      # Python callable: unfused path
+        flags |= nat.F_NORMALISE_O if (self.normalise_o is True and not self._host_reward) else 0
         flags |= nat.F_A_DELTA if (self.a_delta and self.normalise_a) else 0
         flags |= nat.F_R_PENALTY if self.r_penalty else 0
         flags |= nat.F_DONE_ON_VIOLATION if (self.constraint_active and self.done_on_constraint) else 0
@@ -334,7 +380,8 @@ class make_env:
             for i in range(nx):
                 if names[i] not in self.partial_observation:
                     mask |= 1 << i
-        d.obs_zero_mask = mask
+        self._obs_mask_bits = mask
+        d.obs_zero_mask = 0 if self._host_reward else mask
 
         d.noise = nat.NOISE["off"]
         if P.get("noise", False):
@@ -349,7 +396,14 @@ class make_env:
         d.seed, d.env_id0 = self.seed & (2 ** 64 - 1), self.env_id0
 
         d.penalty = 1000.0
-        if self.custom_reward:
+        if self._ocp is not None:
+            d.reward = nat.REWARD["ocp"]
+            d.ocp_R = self._ocp["R"]
+            d.ocp_mode = 2 if self._ocp["delta_u"] else 0
+            for j, k in enumerate(self._sp_keys):
+                i = names.index(k)
+                d.ocp_inv_span[j] = 1.0 / (hi[i] - lo[i])
+        elif self.custom_reward:
             d.reward = nat.REWARD["none"]
         elif self.reward == "SP_reward_fn":
             d.reward = nat.REWARD["sp"]
@@ -408,6 +462,7 @@ class make_env:
         self._sp_dev = torch.from_numpy(np.ascontiguousarray(self._sp_host)).to(dev) if self._sp_host is not None else None
         self._d_dev = torch.from_numpy(np.ascontiguousarray(self._d_host)).to(dev) if self._d_host is not None else None
         self._a_save = z(self._a_lo.shape[0], n) if self.a_delta else None
+        self._u_prev = z(self._a_lo.shape[0], n) if self._ocp is not None else None
         self._tail = z(max(self.NUn, 1), n) if self.NUn else None
         self._done_state = z(n, dtype=torch.uint8)
         self._status = z(n, dtype=torch.uint8)
@@ -455,6 +510,7 @@ class make_env:
             io.g0 = p(self._cons[0])
             io.g = self._cons[self.t + 1].data_ptr() if self.t + 1 < self.N else None
         io.done_state, io.status, io.h_carry, io.n_rhs = p(self._done_state), p(self._status), p(self._h_carry), p(self._n_rhs)
+        io.u_prev = p(self._u_prev)
         return io
 
     # ------------------------------------------------------------------ reset (pcgym.py:263-349)
@@ -545,16 +601,18 @@ class make_env:
         if z is not None:                                    # externally supplied N(0,1) draws, [n_envs, nx]
             z = torch.as_tensor(np.asarray(z, dtype=np.float64)) if not isinstance(z, torch.Tensor) else z
             z = z.to(device=self.device, dtype=torch.float64).reshape(n, self.Nx_oracle).T.contiguous()[None]
+        a_save_old = self._a_save.clone() if (self._host_reward and self.a_delta) else None
+        t_old = self.t
         out = self._launch(self._a_step, 1, want_x=False, z=z)
         obs_soa, r, done, violated = out["obs"][0], out["reward"][0], out["done"][0], out["violated"][0]
-        if self._copy_outputs:
+        if self._copy_outputs or self._host_reward:
             obs_soa, r = obs_soa.clone(), r.clone()
+        if self._host_reward:
+            r, obs_soa = self._custom_reward(obs_soa, self._a_step[0], a_save_old, t_old, violated.bool(), numpy_in)
         self._last_obs = obs_soa
         self.info["obs"] = obs_soa.T
         self.info["violated"] = violated.bool()
         self.info["status"] = self._status
-        if self.custom_reward:
-            r = self._custom_reward(obs_soa, a, violated.bool())
         if n == 1 and numpy_in:
             self.done = bool(done.item())
             return self._single(obs_soa), float(r.item()) if isinstance(r, torch.Tensor) else float(r), self.done, False, self.info
@@ -562,10 +620,47 @@ class make_env:
         self.done = done_b
         return obs_soa.T, r, done_b, torch.zeros_like(done_b), self.info
 
-    def _custom_reward(self, obs_soa, a, violated):
-        raise NotImplementedError(
-            "custom_reward is a Python callable; pass a torch-vectorised function via "
-            "env_params['custom_reward_torch'] (obs_phys [n,Nx], uk [n,Nu], violated [n]) -> [n]")
+    def _uk(self, a_soa, a_save_old, t_old):
+        """Physical input vector uk [Nu, n] of the interval just integrated (pcgym.py:372-414), for custom rewards."""
+        lo = torch.as_tensor(self._a_lo, device=self.device)[:, None]
+        hi = torch.as_tensor(self._a_hi, device=self.device)[:, None]
+        u = a_soa
+        if self.normalise_a is True:
+            u = (u + 1) * (hi - lo) / 2 + lo
+        if self.normalise_a and self.a_delta:
+            u = a_save_old + ((u + 1) * (hi - lo) / 2 + lo)
+        rows = [u]
+        if self.disturbance_active:
+            params = self.model.info()["parameters"]
+            for k in self.model.info()["disturbances"]:
+                if k in self._d_keys:
+                    j = self._d_keys.index(k)
+                    v = self._d_dev[t_old + 1, j] if self._d_per_env else self._d_dev[j, t_old + 1].expand(self.n_envs)
+                else:
+                    v = torch.full((self.n_envs,), float(params[str(k)]), dtype=torch.float64, device=self.device)
+                rows.append(v[None])
+        return torch.cat(rows, dim=0)
+
+    def _custom_reward(self, obs_phys, a_soa, a_save_old, t_old, violated, numpy_in):
+        """Python-callable custom reward (pcgym.py:470-471): `f(env, obs, uk, violated)` with the NOISY
+        physical observation.  A callable cannot be fused, so the kernel ran with reward NONE and emitted
+        physical observations; the callable is evaluated here and the observation is normalised / masked
+        afterwards with torch ops.  n_envs == 1 with numpy input calls it exactly like the reference (numpy
+        vectors, Python bool); batched envs pass torch tensors [n, Nx], [n, Nu], [n]."""
+        uk = self._uk(a_soa, a_save_old, t_old)
+        if self.n_envs == 1 and numpy_in:
+            r = self.custom_reward_f(self, self._single(obs_phys), self._single(uk), bool(violated.item()))
+            r = float(np.asarray(r).reshape(-1)[0])
+        else:
+            r = self.custom_reward_f(self, obs_phys.T, uk.T, violated)
+            r = torch.as_tensor(r, dtype=torch.float64, device=self.device).reshape(self.n_envs)
+        obs = obs_phys
+        if self.normalise_o is True:
+            obs = 2 * (obs - self._o_lo[:, None]) / (self._o_hi[:, None] - self._o_lo[:, None]) - 1
+        for i in range(self.Nx_oracle):
+            if self._obs_mask_bits >> i & 1:
+                obs[i] = 0
+        return r, obs
 
     # ------------------------------------------------------------------ rollout: K intervals, one launch
     def rollout(self, actions, z=None, want_x=True):
@@ -582,6 +677,9 @@ class make_env:
                 a = a.permute(0, 2, 1)
             else:
                 raise ValueError(f"actions must be [K, {nu_a}, {n}] (or [K, {n}, {nu_a}]), got {tuple(a.shape)}")
+        if self._host_reward:
+            raise NotImplementedError("rollout() needs a fused reward: use SP / batch reward or custom_reward="
+                                      "{'kind': 'ocp_tracking', ...}; Python-callable rewards work through step()")
         a = a.to(device=self.device, dtype=torch.float64, non_blocking=True).contiguous()
         K = a.shape[0]
         if self.t + K > self.N - 1:
@@ -603,6 +701,8 @@ class make_env:
             nat.check(nat.lib().pcg_rollout(ctypes.byref(d), ctypes.byref(io), self.n_envs, self.t, K,
                                             ctypes.c_void_p(stream)))
         self.t += K
+        if d.ocp_mode == 2:
+            d.ocp_mode = 1                   # io.u_prev is valid from now on (it survives reset(), as `self.u_prev` does)
         return bufs
 
     def rewind(self, t: int = 0):

@@ -78,6 +78,38 @@ def cstr_batch_reward():
     return p
 
 
+def ocp_reward(R=0.1, delta_u=True):
+    """The "OCP tracking" reward every paper script passes as custom_reward (same mathematics as
+    pc-gym_paper/train_policies/cstr/custom_reward.py:3-39, written independently): squared setpoint error
+    of the o_space-normalised noisy observation, weighted by r_scale, plus R * (change of the a_space-normalised
+    input)^2; negative cost.  Keeps `u_prev` on the env object like the original."""
+    def reward(env, x, u, violated):
+        P = env.env_params
+        names = env.model.info()["states"]
+        lo, hi = np.asarray(P["o_space"]["low"], float), np.asarray(P["o_space"]["high"], float)
+        a_lo, a_hi = np.asarray(P["a_space"]["low"], float), np.asarray(P["a_space"]["high"], float)
+        u = np.asarray(u, float)
+        if not hasattr(env, "u_prev"):
+            env.u_prev = u
+        cost = 0.0
+        for k, sp in P["SP"].items():
+            i = names.index(k)
+            e = (x[i] - sp[env.t]) / (hi[i] - lo[i])
+            cost += e ** 2 * P.get("r_scale", {}).get(k, 1)
+        un, up = (u - a_lo) / (a_hi - a_lo), (env.u_prev - a_lo) / (a_hi - a_lo)
+        cost += np.sum(R * ((un - up) if delta_u else un) ** 2)
+        env.u_prev = u
+        return -float(cost)
+    return reward
+
+
+def cstr_ocp():
+    """pc-gym_paper/train_policies/cstr/cstr_train.py:14-49: CSTR with the OCP tracking custom reward."""
+    p = _cstr_base()
+    p.update(noise=True, noise_percentage=0.001, custom_reward=ocp_reward(0.1))
+    return p
+
+
 def first_order():
     """docs/env/first_order_system.md:38 action range; K=1, tau=0.5 defaults."""
     N = 30
@@ -159,6 +191,7 @@ CASES = {
     "cstr_nonorm_cons": cstr_nonorm_cons,
     "cstr_one_dist": cstr_one_dist,
     "cstr_batch_reward": cstr_batch_reward,
+    "cstr_ocp": cstr_ocp,
     "first_order": first_order,
     "four_tank": four_tank,
     "crystallization": crystallization,

@@ -165,6 +165,9 @@ def gen_traj(outdir):
 def gen_steps(make_env, outdir):
     for name, factory in cases.CASES.items():
         params = factory()
+        if name == "cstr_ocp":      # pin the fused / restated reward against the reference's own function
+            ref = _load("ref_custom_reward", f"{REF}/pc-gym_paper/train_policies/cstr/custom_reward.py")
+            params["custom_reward"] = ref.sp_track_reward
         acts = cases.actions_for(name, params)
         env = make_env(params)
         draws = []

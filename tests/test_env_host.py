@@ -130,3 +130,33 @@ def test_per_env_tables():
     assert env._x0_host.shape == (3, n)
     with pytest.raises(ValueError):
         make_env(dict(p, n_envs=n, x0=np.zeros((3, 3))))
+
+
+def test_custom_reward_forms():
+    p = cases.cstr_ocp()
+    env = make_env(p)                                              # Python callable: unfused path
+    assert env.custom_reward and env._host_reward and env._desc.reward == nat.REWARD["none"]
+    assert not env._desc.flags & nat.F_NORMALISE_O and env.normalise_o is True      # kernel emits physical obs
+    fused = make_env(dict(p, custom_reward={"kind": "ocp_tracking", "R": 0.25, "delta_u": False}))
+    d = fused._desc
+    assert d.reward == nat.REWARD["ocp"] and d.ocp_R == 0.25 and d.ocp_mode == 0 and not fused._host_reward
+    assert abs(d.ocp_inv_span[0] - 1 / 0.3) < 1e-12 and d.flags & nat.F_NORMALISE_O
+    assert make_env(dict(p, custom_reward={"kind": "ocp_tracking"}))._desc.ocp_mode == 2
+    with pytest.raises(ValueError):
+        make_env(dict(p, custom_reward={"kind": "nope"}))
+    with pytest.raises(ValueError):
+        make_env(dict(p, custom_reward=3.0))
+
+
+def test_box_constraint_dict_descriptor():
+    p = cases.cstr_basic()
+    p.update(constraints={"T": [327.0, 321.0], "Tc": [301.0]}, cons_type={"T": ["<=", ">="], "Tc": ["<="]},
+             done_on_cons_vio=True, r_penalty=False)
+    d = make_env(p)._desc
+    assert d.n_con == 3 and d.flags & nat.F_DONE_ON_VIOLATION
+    assert (d.con_gx[0][1], d.con_h[0]) == (1.0, -327.0) and (d.con_gx[1][1], d.con_h[1]) == (-1.0, 321.0)
+    assert (d.con_gu[2][0], d.con_h[2]) == (1.0, -301.0) and d.con_gx[2][1] == 0.0
+    with pytest.raises(KeyError):
+        make_env(dict(p, cons_type=None))
+    with pytest.raises(ValueError):
+        make_env(dict(p, constraints={"Q": [1.0]}, cons_type={"Q": ["<="]}))

@@ -347,3 +347,70 @@ def test_uncertainty_is_observation_only():
     np.testing.assert_allclose(o1[:, 3].cpu().numpy(), obs[:, 3].cpu().numpy())      # carried, never fed to the dynamics
     x = oint.advance_dense("cstr", np.stack([ca0, np.full(n, 330.0)]), np.full((1, n), 298.5), 0.25, n_sub=32)
     assert rel(env._x.cpu().numpy(), x) < 1e-9
+
+
+# ----------------------------------------------------------------------------- custom reward / declarative constraints
+def test_fused_ocp_reward_matches_reference_function(golden_dir):
+    """custom_reward={'kind': 'ocp_tracking'} is evaluated in the kernel; the fixture's rewards were produced by
+    the reference's own sp_track_reward (pc-gym_paper/train_policies/cstr/custom_reward.py) inside its make_env."""
+    g = np.load(os.path.join(golden_dir, "step_cstr_ocp.npz"))
+    p = cases.cstr_ocp()
+    p["custom_reward"] = {"kind": "ocp_tracking", "R": 0.1, "delta_u": True}
+    K = g["actions"].shape[0]
+    # step path, one env
+    env = _env(p, noise_mode="external", integrator=TIGHT)
+    env.reset()
+    for k in range(K):
+        obs, r, done, trunc, info = env.step(g["actions"][k].copy(), z=g["z"][k][None])
+        np.testing.assert_allclose(r, g["reward"][k], rtol=1e-6, atol=1e-10, err_msg=f"reward {k}")
+        np.testing.assert_allclose(obs, g["obs"][k], rtol=5e-7, atol=5e-8)
+    # rollout path, batch of identical envs, one launch; u_prev carries over a reset like `env.u_prev` does
+    n = 64
+    env = _env(p, n_envs=n, noise_mode="external", integrator=TIGHT)
+    env.reset()
+    acts = torch.as_tensor(np.repeat(g["actions"].T[None].transpose(2, 1, 0), n, axis=2))       # [K, 1, n]
+    zz = torch.as_tensor(np.repeat(g["z"][:, :, None], n, axis=2))
+    out = env.rollout(acts, z=zz)
+    np.testing.assert_allclose(out["reward"].cpu().numpy(), np.repeat(g["reward"][:, None], n, axis=1), rtol=1e-6, atol=1e-10)
+    env.reset()
+    out = env.rollout(acts[:1], z=zz[:1])
+    du = (g["actions"][0, 0] - g["actions"][-1, 0]) / 2.0                                        # normalised input change
+    e = (out["x"][0, 0, 0].item() * (1 + 0.001 * g["z"][0, 0]) - 0.85) / 0.3
+    np.testing.assert_allclose(out["reward"][0, 0].item(), -(e * e * 1e3 + 0.1 * du * du), rtol=1e-6)
+
+
+def test_python_callable_custom_reward_batched():
+    p = cases.cstr_basic()
+    n = 128
+    def reward(env, obs, uk, violated):                      # torch-vectorised: [n, Nx], [n, Nu], [n]
+        return -(obs[:, 0] - 0.9) ** 2 - 1e-3 * uk[:, 0] - violated.double()
+    env = _env(p, n_envs=n, custom_reward=reward, noise=False, integrator=TIGHT)
+    env.reset()
+    a = torch.linspace(-1, 1, n, dtype=torch.float64, device="cuda")[:, None]
+    obs, r, done, trunc, info = env.step(a)
+    ca = env._x[0]
+    uk = (a[:, 0] + 1) * 3.5 + 295.0
+    np.testing.assert_allclose(r.cpu().numpy(), (-(ca - 0.9) ** 2 - 1e-3 * uk).cpu().numpy(), rtol=1e-12)
+    np.testing.assert_allclose(obs[:, 0].cpu().numpy(), (2 * (ca - 0.7) / 0.3 - 1).cpu().numpy(), rtol=1e-12)
+    with pytest.raises(NotImplementedError):
+        env.rollout(torch.zeros(2, 1, n, dtype=torch.float64))
+
+
+def test_box_constraint_dict_api():
+    """constraints={'T': [327, 321]}, cons_type={'T': ['<=', '>=']} (oracle.py:127-134, constraint_paper.py:33-35)."""
+    p = cases.cstr_basic()
+    p.update(noise=False, constraints={"T": [327.0, 321.0], "Tc": [301.0]}, cons_type={"T": ["<=", ">="], "Tc": ["<="]},
+             done_on_cons_vio=False, r_penalty=True)
+    n = 256
+    env = _env(p, n_envs=n, integrator=HEADLINE)
+    assert env.n_con == 3
+    env.reset()
+    acts = torch.rand(env.N - 1, 1, n, dtype=torch.float64, generator=torch.Generator().manual_seed(0)) * 2 - 1
+    out = env.rollout(acts)
+    T_ = out["x"][:, 1]
+    u = (acts[:, 0].cuda() + 1) * 3.5 + 295.0
+    want = (T_ > 327.0) | (T_ < 321.0) | (u > 301.0)
+    assert torch.equal(out["violated"].bool(), want) and want.any() and not want.all()
+    g = env.info["cons_info"]
+    np.testing.assert_allclose(g[0, 1:].cpu().numpy(), (T_ - 327.0).cpu().numpy(), rtol=0, atol=1e-12)
+    np.testing.assert_allclose(g[2, 1:].cpu().numpy(), (u - 301.0).cpu().numpy(), rtol=0, atol=1e-12)

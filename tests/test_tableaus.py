@@ -12,14 +12,14 @@ def parse(name):
     src = open(os.path.join(ROOT, "pcgym_b200", "csrc", "tableaus.cuh")).read()
     body = src[src.index(f"struct {name}"):]
     body = body[: body.index("};\n\n") + 2] if "};\n\n" in body else body
-    num = lambda s: float(eval(s.replace("/", "/"), {"__builtins__": {}}))
+    num = lambda s: float(eval(s.strip(), {"__builtins__": {}}))
     A_txt = re.search(r"A\[\d\]\[\d\] = \{(.*?)\};", body, re.S).group(1)
     rows = re.findall(r"\{([^{}]*)\}", A_txt)
-    A = np.array([[num(v) for v in r.split(",")] for r in rows])
+    A = np.array([[num(v) for v in r.split(",") if v.strip()] for r in rows])
     E = None
     m = re.search(r"E\[\d\] = \{(.*?)\};", body, re.S)
     if m:
-        E = np.array([num(v) for v in m.group(1).split(",")])
+        E = np.array([num(v) for v in m.group(1).split(",") if v.strip()])
     return A, E
 
 

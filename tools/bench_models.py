@@ -1,0 +1,75 @@
+#!/usr/bin/env python
+"""Rollout throughput of every registry model (BASELINE configs 2-4 + the rest), information only.
+
+    python tools/bench_models.py [--steps 10]
+
+Prints one JSON line per (model, integrator): env-steps/s, achieved GB/s on the algorithmic rollout bytes of
+SURVEY 8(d) (shared setpoint schedule: 8 B less than the survey's per-env figure), fraction of the measured
+HBM peak.  bench.py remains the contract benchmark (CSTR headline).
+"""
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+from pcgym_b200 import make_env  # noqa: E402
+import test_gpu_parity as T  # noqa: E402  (reuses the per-model batch scenarios)
+
+CONFIGS = [   # model, n_envs, K, integrator
+    ("first_order_system", 65536, 99, {"scheme": "tsit5", "adaptive": False, "n_sub": 1}),
+    ("first_order_system", 1048576, 99, {"scheme": "tsit5", "adaptive": False, "n_sub": 1}),
+    ("cstr", 65536, 99, {"scheme": "tsit5", "adaptive": False, "n_sub": 1}),
+    ("cstr", 524288, 99, {"scheme": "tsit5", "adaptive": False, "n_sub": 1}),
+    ("cstr", 65536, 99, {"scheme": "tsit5", "adaptive": True, "rtol": 1e-8, "atol": 1e-8}),
+    ("four_tank", 65536, 59, {"scheme": "tsit5", "adaptive": False, "n_sub": 2}),
+    ("crystallization", 65536, 29, {"scheme": "tsit5", "adaptive": False, "n_sub": 8}),
+    ("biofilm_reactor", 32768, 19, {"scheme": "tsit5", "adaptive": True, "rtol": 1e-8, "atol": 1e-10}),
+    ("multistage_extraction", 32768, 59, {"scheme": "tsit5", "adaptive": True, "rtol": 1e-8, "atol": 1e-10}),
+]
+
+
+def bytes_per_env_step(env):
+    nx, nu = env.Nx_oracle, env._a_lo.shape[0]
+    return 8 * nu + 8 * (nx + env._n_obs + 1 + env.n_con) + 2
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--steps", type=int, default=10)
+    args = ap.parse_args()
+    peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(
+        os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
+    for model, n, K, integ in CONFIGS:
+        params, x0, acts, key, sp = T.batch_setup(model, n, K)
+        params = dict(params, integrator=integ, noise=True, noise_percentage=0.001)
+        env = make_env(params)
+        env.reset()
+        a = torch.as_tensor(acts, device="cuda")
+        for _ in range(3):
+            env.rewind(); env.rollout(a)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            env.rewind(); env.rollout(a)
+        e1.record(); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / args.steps
+        b = bytes_per_env_step(env)
+        rate = n * K / (ms * 1e-3)
+        rhs = float(env.rhs_evaluations.double().mean()) / (K * (args.steps + 3))
+        print(json.dumps({"model": model, "n_envs": n, "intervals": K, "integrator": integ, "ms_per_launch": round(ms, 4),
+                          "env_steps_per_s": rate, "bytes_per_env_step": b, "GBps": rate * b / 1e9,
+                          "hbm_frac": rate * b / 1e9 / peak, "rhs_evals_per_interval": round(rhs, 1),
+                          "status_nonzero": int((env.status != 0).sum())}), flush=True)
+        del env, a
+        torch.cuda.empty_cache()
+
+
+if __name__ == "__main__":
+    main()
