@@ -40,7 +40,7 @@ K_STEPS = N_HORIZON - 1
 # SURVEY 8(d) quotes 82 B because it assumes per-env setpoint tensors (8 B more read per env-step); the
 # headline uses the reference's shared setpoint schedule, which costs no per-env traffic.
 BYTES_PER_ENV_STEP = 74
-NCU_DRAM_BYTES_PER_LAUNCH = 53387520 + 372079872      # profiles/r1_cstr_v5_ncu_summary.txt
+NCU_DRAM_BYTES_PER_LAUNCH = 53325056 + 371124224      # profiles/r1_cstr_v6_mono_ncu_summary.txt
 HEADLINE_INTEGRATOR = {"scheme": "tsit5", "adaptive": False, "n_sub": 1}
 
 
@@ -231,6 +231,7 @@ def main():
         t_all1.record()
         barrier()
         launches = lib.pcg_launch_count() - l0
+        kernel_name = "pcg::" + lib.pcg_last_kernel().decode() + " <cstr, tsit5, %s>" % args.noise_mode
         # keep the GPU busy a little longer so the 100 ms sampler sees the loaded clocks
         t_end = time.perf_counter() + 0.6
         while time.perf_counter() < t_end:
@@ -305,11 +306,11 @@ def main():
                    "parallelism": f"env-sharded x{world}, no collective"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": NCU_DRAM_BYTES_PER_LAUNCH if n == N_ENVS else None,
-                     "traffic_note": "dram__bytes_read+write.sum of one launch, profiles/r1_cstr_v5_ncu_summary.txt "
+                     "traffic_note": "dram__bytes_read+write.sum of one launch, profiles/r1_cstr_v6_mono_ncu_summary.txt "
                                      "(~55 MB of the stores are still in L2 at kernel end)",
                      "algorithmic_bytes": BYTES_PER_ENV_STEP * env_steps_per_launch,
                      "peak_source": peak_src, "bytes_per_env_step": BYTES_PER_ENV_STEP,
-                     "kernel_ms": kern_ms_max, "kernel": "pcg::fast_rollout_kernel<Cstr,Tsit5,PHILOX,2>",
+                     "kernel_ms": kern_ms_max, "kernel": kernel_name,
                      "fp64_note": "FP64-pipe/latency bound, not HBM bound: see profiles/README.md"},
         "cpu_baseline": cpu,
         "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

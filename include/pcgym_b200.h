@@ -218,6 +218,12 @@ int pcg_step(const pcg_desc* d, const pcg_io* io, int64_t n_env, int64_t t, void
 int pcg_rollout(const pcg_desc* d, const pcg_io* io, int64_t n_env, int64_t t0, int64_t k_steps,
                 void* cuda_stream);
 
+/* The measurement-noise transform in isolation (pcgym.py:453-466 draws np.random.normal; here two 32-bit Philox
+ * words -> two N(0,1), see csrc/philox.cuh): z0[i], z1[i] from (w0[i], w1[i]) for i < n, device pointers.
+ * f32 != 0 selects the PCG_NOISE_PHILOX_F32 evaluation.  Lets a caller check the documented draw exactly. */
+int pcg_normal_pairs(const uint32_t* w0, const uint32_t* w1, double* z0, double* z1, int64_t n, int f32,
+                     void* cuda_stream);
+
 /* Number of kernel launches issued by this library since load (diagnostics for bench.py). */
 int64_t pcg_launch_count(void);
 
@@ -225,6 +231,10 @@ int64_t pcg_launch_count(void);
  * of the most recent failure on the calling thread. */
 const char* pcg_strerror(int status);
 const char* pcg_last_cuda_error(void);
+
+/* Kernel family the calling thread's most recent pcg_step / pcg_rollout launched (diagnostics: the library
+ * picks between the generic, the software-pipelined and the warp-specialised kernel per configuration). */
+const char* pcg_last_kernel(void);
 
 #ifdef __cplusplus
 }

@@ -87,9 +87,11 @@ SYMBOLS = {
     "pcg_model_param_default": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_double)]),
     "pcg_step": (C.c_int, [C.POINTER(Desc), C.POINTER(IO), C.c_int64, C.c_int64, C.c_void_p]),
     "pcg_rollout": (C.c_int, [C.POINTER(Desc), C.POINTER(IO), C.c_int64, C.c_int64, C.c_int64, C.c_void_p]),
+    "pcg_normal_pairs": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]),
     "pcg_launch_count": (C.c_int64, []),
     "pcg_strerror": (C.c_char_p, [C.c_int]),
     "pcg_last_cuda_error": (C.c_char_p, []),
+    "pcg_last_kernel": (C.c_char_p, []),
 }
 
 _lib = None

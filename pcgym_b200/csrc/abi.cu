@@ -43,6 +43,17 @@ const ModelInfo kModels[PCG_MODEL_COUNT] = {
     info<pcg::Biofilm>(kBfN, kBfD, pcg::launch_biofilm),
 };
 
+// the measurement-noise transform on caller-supplied Philox words (pcg_normal_pairs)
+__global__ void normal_pairs_kernel(const uint32_t* w0, const uint32_t* w1, double* z0, double* z1, int64_t n, bool f32) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double a, b;
+  if (f32) pcg::normal_pair_u32<true>(w0[i], w1[i], a, b);
+  else pcg::normal_pair_u32<false>(w0[i], w1[i], a, b);
+  z0[i] = a;
+  z1[i] = b;
+}
+
 std::atomic<int64_t> g_launches{0};
 thread_local char t_cuda_err[256] = "";
 
@@ -139,6 +150,21 @@ int pcg_step(const pcg_desc* d, const pcg_io* io, int64_t n_env, int64_t t, void
   return pcg_rollout(d, io, n_env, t, 1, cuda_stream);
 }
 
+int pcg_normal_pairs(const uint32_t* w0, const uint32_t* w1, double* z0, double* z1, int64_t n, int f32,
+                     void* cuda_stream) {
+  if (!w0 || !w1 || !z0 || !z1) return PCG_E_NULL;
+  if (n < 1 || n > (int64_t{1} << 31) - 256) return PCG_E_RANGE;
+  const unsigned grid = static_cast<unsigned>((n + 255) / 256);
+  normal_pairs_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(cuda_stream)>>>(w0, w1, z0, z1, n, f32 != 0);
+  const cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    std::strncpy(t_cuda_err, cudaGetErrorString(e), sizeof(t_cuda_err) - 1);
+    return PCG_E_CUDA;
+  }
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return PCG_OK;
+}
+
 int64_t pcg_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 const char* pcg_strerror(int status) {
@@ -157,5 +183,7 @@ const char* pcg_strerror(int status) {
 }
 
 const char* pcg_last_cuda_error(void) { return t_cuda_err; }
+
+const char* pcg_last_kernel(void) { return pcg::t_last_kernel; }
 
 }  // extern "C"

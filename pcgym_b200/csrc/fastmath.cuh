@@ -82,6 +82,21 @@ PCG_DEV double exp_sat(double x) {
   return p * __hiloint2double((n + 1023) << 20, 0);
 }
 
+// Same function with the polynomial in Horner form: 10 dependent DFMA instead of 13 DFMA/DMUL at depth 4.
+// Three FP64 issue slots cheaper per call; used where other warps hide the longer dependency chain.
+PCG_DEV double exp_sat_horner(double x) {
+  const double t = fma(x, kMC.log2e, kMC.shift);
+  int n = __double2loint(t);
+  const double nf = t - kMC.shift;
+  double r = fma(nf, kMC.ln2_hi, x);
+  r = fma(nf, kMC.ln2_lo, r);
+  n = max(-1000, min(1000, n));
+  double p = kMC.ex[10];
+#pragma unroll
+  for (int i = 9; i >= 0; --i) p = fma(p, r, kMC.ex[i]);
+  return p * __hiloint2double((n + 1023) << 20, 0);
+}
+
 // ln(u) for a positive NORMAL double (the Box-Muller argument is (k + 1/2) 2^-53, never 0 or denormal).
 // u = m 2^e with m in [sqrt(1/2), sqrt(2)); ln m = 2 atanh(s), s = (m-1)/(m+1), |s| <= 0.1716;
 // odd series to s^19 (remainder < 2e-16), Estrin form.

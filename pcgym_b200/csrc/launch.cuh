@@ -5,11 +5,14 @@
 
 #include <cstdlib>
 
-#include "rollout_fast.cuh"
+#include "rollout_ws.cuh"
 
 namespace pcg {
 
 using launch_fn = cudaError_t (*)(const pcg_desc&, const pcg_io&, int64_t, int, int, cudaStream_t);
+
+// which kernel family the calling thread launched last (pcg_last_kernel, diagnostics for bench.py)
+inline thread_local const char* t_last_kernel = "";
 
 inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
@@ -36,6 +39,7 @@ cudaError_t launch_one(const pcg_desc& d, const pcg_io& io, int64_t n_env, int t
   const unsigned grid = static_cast<unsigned>((threads + kBlock - 1) / kBlock);
   const Derived<M, TB> dv = make_derived<M, TB>(d);
   rollout_kernel<M, TB, ADAPTIVE, GENERAL, EPT><<<grid, kBlock, 0, s>>>(d, io, dv, n_env, t0, k_steps);
+  t_last_kernel = EPT == 2 ? "rollout_kernel (generic, 2 envs/thread)" : "rollout_kernel (generic, 1 env/thread)";
   return cudaGetLastError();
 }
 
@@ -61,8 +65,25 @@ inline bool fast_ok(const pcg_desc& d, const pcg_io& io) {
   return !off;
 }
 
+// The straight-line kernels apply every option arithmetically: the descriptor they see has the options folded
+// into its coefficients (scale 1 / offset 0 when a normalisation is off, scale 0 / offset 0 for a masked
+// observation -- a non-finite masked state then reads NaN instead of 0 --, penalty 0 without r_penalty).
+template <class M>
+inline pcg_desc fold_desc(const pcg_desc& d) {
+  pcg_desc f = d;
+  if (!(d.flags & PCG_F_NORMALISE_A))
+    for (int j = 0; j < PCG_MAX_NU; ++j) { f.a_scale[j] = 1.0; f.a_off[j] = 0.0; }
+  for (int i = 0; i < PCG_MAX_OBS; ++i) {
+    if (!(d.flags & PCG_F_NORMALISE_O)) { f.o_scale[i] = 1.0; f.o_off[i] = 0.0; }
+    if (i < 32 && (d.obs_zero_mask >> i & 1u)) { f.o_scale[i] = 0.0; f.o_off[i] = 0.0; }
+  }
+  if (!(d.flags & PCG_F_R_PENALTY)) f.penalty = 0.0;
+  return f;
+}
+
 template <class M, class TB, int EPT>
-cudaError_t launch_fast(const pcg_desc& d, const pcg_io& io, int64_t n_env, int t0, int k_steps, cudaStream_t s) {
+cudaError_t launch_fast(const pcg_desc& d0, const pcg_io& io, int64_t n_env, int t0, int k_steps, cudaStream_t s) {
+  const pcg_desc d = fold_desc<M>(d0);
   const int64_t threads = (n_env + EPT - 1) / EPT;
   const unsigned grid = static_cast<unsigned>((threads + kBlock - 1) / kBlock);
   const Derived<M, TB> dv = make_derived<M, TB>(d);
@@ -77,15 +98,65 @@ cudaError_t launch_fast(const pcg_desc& d, const pcg_io& io, int64_t n_env, int 
       fast_rollout_kernel<M, TB, PCG_NOISE_PHILOX_F32, EPT><<<grid, kBlock, 0, s>>>(d, io, dv, n_env, t0, k_steps);
       break;
   }
+  t_last_kernel = EPT == 2 ? "fast_rollout_kernel (software-pipelined, 2 envs/thread)"
+                           : "fast_rollout_kernel (software-pipelined, 1 env/thread)";
+  return cudaGetLastError();
+}
+
+// warp-specialised kernel (rollout_ws.cuh): models that opt in (M::WS > 0 = pairs per CTA), 128-bit rows.
+// PCG_WS=0 falls back to the monolithic fast kernel, PCG_WS=1|2 picks the pairs per CTA (profiling knobs).
+inline int ws_override() {
+  static const int v = [] { const char* e = std::getenv("PCG_WS"); return e ? std::atoi(e) : -1; }();
+  return v;
+}
+
+// Which straight-line kernel for a batch (profiles/r1_sweep_envs.txt, 148 SMs): the warp-specialised kernel
+// keeps 3-4 light warps per scheduler and wins when the batch fills the SMs evenly or thinly (<= 6 pairs of 64
+// envs per SM) and again from ~10 pairs per SM up (16 resident warps against the monolithic kernel's 8); in
+// between (the 7th and 8th pair land two-deep on two of the four schedulers) the 255-register kernel is ahead.
+inline bool ws_preferred(int64_t n_env) {
+  static const int sms = [] {
+    int dev = 0, v = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    return v > 0 ? v : 148;
+  }();
+  const double pairs_per_sm = static_cast<double>(n_env) / (64.0 * sms);
+  return pairs_per_sm <= 6.0 || pairs_per_sm > 8.5;
+}
+
+template <class M, class TB, int W>
+cudaError_t launch_ws(const pcg_desc& d0, const pcg_io& io, int64_t n_env, int t0, int k_steps, cudaStream_t s) {
+  const pcg_desc d = fold_desc<M>(d0);
+  const unsigned grid = static_cast<unsigned>((n_env + 64 * W - 1) / (64 * W));
+  const Derived<M, TB> dv = make_derived<M, TB>(d);
+  switch (d.noise) {
+    case PCG_NOISE_OFF:
+      ws_rollout_kernel<M, TB, PCG_NOISE_OFF, W><<<grid, 64 * W, 0, s>>>(d, io, dv, n_env, t0, k_steps);
+      break;
+    case PCG_NOISE_PHILOX:
+      ws_rollout_kernel<M, TB, PCG_NOISE_PHILOX, W><<<grid, 64 * W, 0, s>>>(d, io, dv, n_env, t0, k_steps);
+      break;
+    default:
+      ws_rollout_kernel<M, TB, PCG_NOISE_PHILOX_F32, W><<<grid, 64 * W, 0, s>>>(d, io, dv, n_env, t0, k_steps);
+      break;
+  }
+  t_last_kernel = "ws_rollout_kernel (warp-specialised integrator/finisher pairs)";
   return cudaGetLastError();
 }
 
 template <class M, class TB, bool ADAPTIVE, bool GENERAL>
 cudaError_t launch_e(const pcg_desc& d, const pcg_io& io, int64_t n_env, int t0, int k_steps, cudaStream_t s) {
-  const bool two = M::EPT == 2 && ept_override() != 1 && vector_ok(io, n_env);
+  // two envs per thread share one Philox block, which needs an even global id for the first of them
+  const bool two = M::EPT == 2 && ept_override() != 1 && vector_ok(io, n_env) && d.env_id0 % 2 == 0;
   if constexpr (!ADAPTIVE && !GENERAL) {
     if (fast_ok<M>(d, io)) {
       if constexpr (M::EPT == 2) {
+        if constexpr (M::WS > 0) {
+          const int w = ws_override() < 0 ? (ws_preferred(n_env) ? M::WS : 0) : ws_override();
+          // the integrator warps run the model's WsModel (cstr: Horner-form exp, 3 FP64 issue slots fewer per RHS)
+          if (two && w == 1) return launch_ws<typename M::WsModel, TB, 1>(d, io, n_env, t0, k_steps, s);
+          if (two && w == 2) return launch_ws<typename M::WsModel, TB, 2>(d, io, n_env, t0, k_steps, s);
+        }
         if (two) return launch_fast<M, TB, 2>(d, io, n_env, t0, k_steps, s);
       }
       return launch_fast<M, TB, 1>(d, io, n_env, t0, k_steps, s);

@@ -48,11 +48,24 @@ struct Cstr {
   static constexpr int d_param[ND] = {8, 9};      // theta index of each disturbance default
   static constexpr int EPT = 2;                   // environments per thread (ILP 2 on the FP64 pipe)
   static constexpr int MIN_BLOCKS = 4, MIN_BLOCKS_EPT1 = 7;   // 7 x 64 threads x 144 regs: 65 536 envs in one wave
+  static constexpr int WS = 1;                    // warp-specialised kernel: integrator/finisher pairs per CTA
+  using WsModel = struct CstrH;                   // RHS variant its integrator warps run
   PCG_DEV static void rhs(const P& p, const Aux& a, const double* x, const double*, double* dx) {
     const double ca = x[0], T = x[1];
     const double rate = exp_sat(fma(p.neg_ear, rcp_nr(T), p.ln_k0)) * ca;        // :52
     dx[0] = fma(-p.thru, ca, a.feed_c) - rate;                                   // :53
     dx[1] = fma(p.c_heat, rate, fma(p.c_T, T, a.heat0));                         // :54-58
+  }
+};
+
+// cstr with the Horner-form exponential (integrator warps of the warp-specialised kernel)
+struct CstrH : Cstr {
+  using WsModel = CstrH;
+  PCG_DEV static void rhs(const P& p, const Aux& a, const double* x, const double*, double* dx) {
+    const double ca = x[0], T = x[1];
+    const double rate = exp_sat_horner(fma(p.neg_ear, rcp_nr(T), p.ln_k0)) * ca;
+    dx[0] = fma(-p.thru, ca, a.feed_c) - rate;
+    dx[1] = fma(p.c_heat, rate, fma(p.c_T, T, a.heat0));
   }
 };
 
@@ -65,7 +78,7 @@ struct FirstOrder {
   struct Aux {};
   PCG_DEV static void prep(const P&, const double*, Aux&) {}
   static constexpr int d_param[1] = {0};
-  static constexpr int EPT = 2, MIN_BLOCKS = 8, MIN_BLOCKS_EPT1 = 8;
+  static constexpr int EPT = 2, MIN_BLOCKS = 8, MIN_BLOCKS_EPT1 = 8, WS = 0;
   PCG_DEV static void rhs(const P& p, const Aux&, const double* x, const double* u, double* dx) {
     dx[0] = fma(p.K, u[0], -x[0]) * p.inv_tau;                   // :322
   }
@@ -92,7 +105,7 @@ struct Extraction {
   struct Aux {};
   PCG_DEV static void prep(const P&, const double*, Aux&) {}
   static constexpr int d_param[ND] = {5, 6};
-  static constexpr int EPT = 1, MIN_BLOCKS = 4, MIN_BLOCKS_EPT1 = 4;
+  static constexpr int EPT = 1, MIN_BLOCKS = 4, MIN_BLOCKS_EPT1 = 4, WS = 0;
   PCG_DEV static void rhs(const P& p, const Aux&, const double* x, const double* u, double* dx) {
     const double L = u[0], G = u[1], X0 = u[2], Y6 = u[3];
 #pragma unroll
@@ -130,7 +143,7 @@ struct FourTank {
   struct Aux {};
   PCG_DEV static void prep(const P&, const double*, Aux&) {}
   static constexpr int d_param[1] = {0};
-  static constexpr int EPT = 1, MIN_BLOCKS = 4, MIN_BLOCKS_EPT1 = 4;
+  static constexpr int EPT = 1, MIN_BLOCKS = 4, MIN_BLOCKS_EPT1 = 4, WS = 0;
   PCG_DEV static void rhs(const P& p, const Aux&, const double* x, const double* u, double* dx) {
     const double s1 = sqrt(p.g2 * x[0]), s2 = sqrt(p.g2 * x[1]);   // NaN for h < 0, as the reference
     const double s3 = sqrt(p.g2 * x[2]), s4 = sqrt(p.g2 * x[3]);
@@ -154,7 +167,7 @@ struct Crystallization {
   struct Aux {};
   PCG_DEV static void prep(const P&, const double*, Aux&) {}
   static constexpr int d_param[ND] = {0, 4, -1};   // "UA" is not a parameter of this model
-  static constexpr int EPT = 1, MIN_BLOCKS = 4, MIN_BLOCKS_EPT1 = 4;
+  static constexpr int EPT = 1, MIN_BLOCKS = 4, MIN_BLOCKS_EPT1 = 4, WS = 0;
   PCG_DEV static void rhs(const P& p, const Aux&, const double* x, const double* u, double* dx) {
     const double mu0 = x[0], mu1 = x[1], mu2 = x[2], mu3 = x[3], conc = x[4];
     const double TK = u[0] + 273.15;
@@ -198,7 +211,7 @@ struct Biofilm {
   struct Aux {};
   PCG_DEV static void prep(const P&, const double*, Aux&) {}
   static constexpr int d_param[1] = {0};
-  static constexpr int EPT = 1, MIN_BLOCKS = 4, MIN_BLOCKS_EPT1 = 4;
+  static constexpr int EPT = 1, MIN_BLOCKS = 4, MIN_BLOCKS_EPT1 = 4, WS = 0;
   PCG_DEV static void rhs(const P& p, const Aux&, const double* x, const double* u, double* dx) {
     const double F = u[0], Fr = u[1];
     const double frv = Fr * p.inv_v, fra = Fr * p.inv_va, fa = F * p.inv_va;

@@ -38,12 +38,10 @@ fast_rollout_kernel(const __grid_constant__ pcg_desc d, const __grid_constant__ 
   if (env0 >= n) return;
 
   const int flags = d.flags;
-  const bool norm_a = flags & PCG_F_NORMALISE_A, norm_o = flags & PCG_F_NORMALISE_O;
-  const bool penal = flags & PCG_F_R_PENALTY, done_on_v = flags & PCG_F_DONE_ON_VIOLATION;
+  const bool done_on_v = flags & PCG_F_DONE_ON_VIOLATION;
   const int nsp = d.nsp, n_con = d.n_con, n_obs = NX + nsp;
-  const double pen = penal ? d.penalty : 0.0;
-  const uint32_t zmask = d.obs_zero_mask;
-  const uint2 key = make_uint2(static_cast<uint32_t>(d.seed), static_cast<uint32_t>(d.seed >> 32));
+  const double pen = d.penalty;
+  const PhiloxKeys& key = dv.rk;
   const int t_last = d.N - 1;
 
   double x[EPT][NX];
@@ -85,7 +83,7 @@ fast_rollout_kernel(const __grid_constant__ pcg_desc d, const __grid_constant__ 
 #pragma unroll
     for (int e = 0; e < EPT; ++e) {
 #pragma unroll
-      for (int j = 0; j < NU; ++j) uk[e][j] = norm_a ? fma(a_raw[j][e], d.a_scale[j], d.a_off[j]) : a_raw[j][e];
+      for (int j = 0; j < NU; ++j) uk[e][j] = fma(a_raw[j][e], d.a_scale[j], d.a_off[j]);
 #pragma unroll
       for (int i = 0; i < ND; ++i) uk[e][NU + i] = d.d_default[i];
     }
@@ -150,8 +148,7 @@ fast_rollout_kernel(const __grid_constant__ pcg_desc d, const __grid_constant__ 
       for (int e = 0; e < EPT; ++e) {
         v[e] = xe[e][i];
         double ox = (NOISE != PCG_NOISE_OFF) ? fma(o.z[e][i] * xe[e][i], d.noise_pct[i], xe[e][i]) : xe[e][i];
-        ox = norm_o ? fma(ox, d.o_scale[i], d.o_off[i]) : ox;                  // pcgym.py:483-493
-        w[e] = (zmask >> i & 1u) ? 0.0 : ox;                                   // pcgym.py:495-498
+        w[e] = fma(ox, d.o_scale[i], d.o_off[i]);          // pcgym.py:483-493, 495-498 (folded: fold_desc)
       }
       st_row<EPT>(px + i * n, v);
       st_row<EPT>(po + i * n, w);
@@ -161,7 +158,7 @@ fast_rollout_kernel(const __grid_constant__ pcg_desc d, const __grid_constant__ 
       double w[EPT];
 #pragma unroll
       for (int e = 0; e < EPT; ++e)
-        w[e] = norm_o ? fma(o.sp_cur[j][e], d.o_scale[NX + j], d.o_off[NX + j]) : o.sp_cur[j][e];
+        w[e] = fma(o.sp_cur[j][e], d.o_scale[NX + j], d.o_off[NX + j]);
       if (j < nsp) st_row<EPT>(po + (NX + j) * n, w);
     }
     st_row<EPT>(pr, r);
@@ -209,31 +206,16 @@ fast_rollout_kernel(const __grid_constant__ pcg_desc d, const __grid_constant__ 
     for (int e = 0; e < EPT; ++e)
 #pragma unroll
       for (int i = 0; i < NX; ++i) cur.z[e][i] = 0.0;
-    if constexpr (NOISE == PCG_NOISE_PHILOX) {
+    if constexpr (NOISE != PCG_NOISE_OFF) {
+      const uint64_t gid0 = static_cast<uint64_t>(d.env_id0 + env0);           // even: launch.cuh checks env_id0
 #pragma unroll
-      for (int e = 0; e < EPT; ++e) {
-        const uint64_t gid = static_cast<uint64_t>(d.env_id0 + env0 + e);
+      for (int i = 0; i < NX; i += 2) {
+        double za[EPT], zb[EPT];
+        draw_state_pair<EPT, NOISE == PCG_NOISE_PHILOX_F32>(gid0, static_cast<uint32_t>(cur.t_new), i / 2, key, za, zb);
 #pragma unroll
-        for (int i = 0; i < NX; i += 2) {
-          double z0, z1;
-          normal_pair_f64(philox4x32_10(make_uint4(static_cast<uint32_t>(gid), static_cast<uint32_t>(gid >> 32),
-                                                   static_cast<uint32_t>(cur.t_new), i / 2), key), z0, z1);
-          cur.z[e][i] = z0;
-          if (i + 1 < NX) cur.z[e][i + 1] = z1;
-        }
-      }
-    } else if constexpr (NOISE == PCG_NOISE_PHILOX_F32) {
-#pragma unroll
-      for (int e = 0; e < EPT; ++e) {
-        const uint64_t gid = static_cast<uint64_t>(d.env_id0 + env0 + e);
-#pragma unroll
-        for (int i = 0; i < NX; i += 4) {
-          double zq[4];
-          normal_quad_f32(philox4x32_10(make_uint4(static_cast<uint32_t>(gid), static_cast<uint32_t>(gid >> 32),
-                                                   static_cast<uint32_t>(cur.t_new), i / 4), key), zq);
-#pragma unroll
-          for (int q = 0; q < 4; ++q)
-            if (i + q < NX) cur.z[e][i + q] = zq[q];
+        for (int e = 0; e < EPT; ++e) {
+          cur.z[e][i] = za[e];
+          if (i + 1 < NX) cur.z[e][i + 1] = zb[e];
         }
       }
     }
@@ -252,6 +234,7 @@ fast_rollout_kernel(const __grid_constant__ pcg_desc d, const __grid_constant__ 
       for (int i = 0; i < NX; ++i) x_prev_end[e][i] = x[e][i];
   };
   interval(0, std::false_type{});
+  // unrolled by two so the hand-over registers (prev / x_prev_end) alternate names instead of being copied
 #pragma unroll 1
   for (int k = 1; k < k_steps; ++k) interval(k, std::true_type{});
   epilogue(prev, x_prev_end);

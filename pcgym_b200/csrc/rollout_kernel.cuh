@@ -39,6 +39,7 @@ struct Derived {
   double a[TB::S][TB::S];    // raw coefficients (adaptive mode, h varies per lane)
   double b[TB::S];
   double e[TB::S + 1];
+  PhiloxKeys rk;             // Philox round keys of desc.seed
 };
 
 template <class M, class TB>
@@ -55,6 +56,7 @@ inline Derived<M, TB> make_derived(const pcg_desc& d) {
     v.hb[i] = h * v.b[i];
   }
   for (int i = 0; i <= TB::S; ++i) v.e[i] = TB::e(i);
+  v.rk = make_round_keys(d.seed);
   return v;
 }
 
@@ -336,7 +338,7 @@ rollout_kernel(const __grid_constant__ pcg_desc d, const __grid_constant__ pcg_i
   double a_nxt[NU][EPT];
 #pragma unroll
   for (int j = 0; j < NU; ++j) ld_row<EPT>(pa + j * n, a_nxt[j]);
-  const uint2 key = make_uint2(static_cast<uint32_t>(d.seed), static_cast<uint32_t>(d.seed >> 32));
+  const PhiloxKeys& key = dv.rk;
 
 #pragma unroll 1
   for (int k = 0; k < k_steps; ++k) {
@@ -469,31 +471,17 @@ rollout_kernel(const __grid_constant__ pcg_desc d, const __grid_constant__ pcg_i
       for (int e = 0; e < EPT; ++e)
 #pragma unroll
         for (int i = 0; i < NX; ++i) z[e][i] = 0.0;
-      if (noise == PCG_NOISE_PHILOX) {
+      if (noise == PCG_NOISE_PHILOX || noise == PCG_NOISE_PHILOX_F32) {
+        const uint64_t gid0 = static_cast<uint64_t>(d.env_id0 + env0);
 #pragma unroll
-        for (int e = 0; e < EPT; ++e) {
-          const uint64_t gid = static_cast<uint64_t>(d.env_id0 + env0 + e);
+        for (int i = 0; i < NX; i += 2) {
+          double za[EPT], zb[EPT];
+          if (noise == PCG_NOISE_PHILOX) draw_state_pair<EPT, false>(gid0, static_cast<uint32_t>(t_new), i / 2, key, za, zb);
+          else draw_state_pair<EPT, true>(gid0, static_cast<uint32_t>(t_new), i / 2, key, za, zb);
 #pragma unroll
-          for (int i = 0; i < NX; i += 2) {
-            double z0, z1;
-            normal_pair_f64(philox4x32_10(make_uint4(static_cast<uint32_t>(gid), static_cast<uint32_t>(gid >> 32),
-                                                     static_cast<uint32_t>(t_new), i / 2), key), z0, z1);
-            z[e][i] = z0;
-            if (i + 1 < NX) z[e][i + 1] = z1;
-          }
-        }
-      } else if (noise == PCG_NOISE_PHILOX_F32) {
-#pragma unroll
-        for (int e = 0; e < EPT; ++e) {
-          const uint64_t gid = static_cast<uint64_t>(d.env_id0 + env0 + e);
-#pragma unroll
-          for (int i = 0; i < NX; i += 4) {
-            double zq[4];
-            normal_quad_f32(philox4x32_10(make_uint4(static_cast<uint32_t>(gid), static_cast<uint32_t>(gid >> 32),
-                                                     static_cast<uint32_t>(t_new), i / 4), key), zq);
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-              if (i + q < NX) z[e][i + q] = zq[q];
+          for (int e = 0; e < EPT; ++e) {
+            z[e][i] = za[e];
+            if (i + 1 < NX) z[e][i + 1] = zb[e];
           }
         }
       } else if (noise == PCG_NOISE_EXTERNAL) {

@@ -236,10 +236,12 @@ def test_philox_known_answers_host_model():
         [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]
 
 
-def test_device_noise_is_philox_boxmuller():
-    """z recovered from the kernel's noisy observation equals Philox4x32-10 + Box-Muller for (seed, env, t)."""
+@pytest.mark.parametrize("n,id0", [(8, 1000), (7, 1001)])      # even batch: 2 envs/thread kernels; odd: 1 env/thread
+def test_device_noise_is_philox_boxmuller(n, id0):
+    """z recovered from the kernel's noisy observation equals the documented draw (csrc/philox.cuh): Philox4x32-10
+    block of (env pair gid >> 1, t, state pair), words (2p, 2p+1) for env parity p, 32-bit uniforms, Box-Muller."""
     params = cases.cstr_basic()
-    seed, id0, n = 0x1234567_89ABCDEF, 1000, 8
+    seed = 0x1234567_89ABCDEF
     env = _env(params, n_envs=n, seed=seed, env_id0=id0, normalise_o=False, integrator=HEADLINE)
     env.reset()
     a = torch.zeros(3, 1, n, dtype=torch.float64)
@@ -250,11 +252,52 @@ def test_device_noise_is_philox_boxmuller():
         z = (out["obs"][k, :2].cpu().numpy() - x) / (x * pct)
         for e in range(n):
             gid = id0 + e
-            r = philox_py([gid & 0xFFFFFFFF, gid >> 32, k + 1, 0], [seed & 0xFFFFFFFF, seed >> 32])
-            u0 = (((r[1] << 32 | r[0]) >> 11) + 0.5) * 2.0 ** -53
-            u1 = (((r[3] << 32 | r[2]) >> 11) + 0.5) * 2.0 ** -53
+            r = philox_py([(gid >> 1) & 0xFFFFFFFF, gid >> 33, k + 1, 0], [seed & 0xFFFFFFFF, seed >> 32])
+            w0, w1 = r[2 * (gid & 1)], r[2 * (gid & 1) + 1]
+            u0, u1 = (w0 + 0.5) * 2.0 ** -32, (w1 + 0.5) * 2.0 ** -32
             rad = np.sqrt(-2 * np.log(u0))
             np.testing.assert_allclose(z[:, e], [rad * np.cos(2 * np.pi * u1), rad * np.sin(2 * np.pi * u1)], rtol=0, atol=2e-9)
+
+
+def test_normal_transform_accuracy_over_the_word_range():
+    """pcg_normal_pairs: the fp64 Box-Muller of csrc/philox.cuh (table log, Goldschmidt sqrt, integer quadrant
+    reduction) against numpy on edge words and 2^20 random ones; the fp32 evaluation to fp32 accuracy."""
+    from pcgym_b200 import _native as nat
+    rng = np.random.default_rng(5)
+    edge = np.array([0, 1, 2, 0x1fffffff, 0x20000000, 0x20000001, 0x3fffffff, 0x40000000, 0x5fffffff, 0x60000000,
+                     0x7fffffff, 0x80000000, 0x9fffffff, 0xa0000000, 0xbfffffff, 0xc0000000, 0xdfffffff, 0xe0000000,
+                     0xfffffffe, 0xffffffff, 0x6a09e667, 0xb504f333, 0xb504f334], dtype=np.uint64)
+    w0 = np.concatenate([np.repeat(edge, len(edge)), rng.integers(0, 2 ** 32, 1 << 20, dtype=np.uint64)])
+    w1 = np.concatenate([np.tile(edge, len(edge)), rng.integers(0, 2 ** 32, 1 << 20, dtype=np.uint64)])
+    n = w0.size
+    dw0 = torch.from_numpy(w0.astype(np.uint32).view(np.int32)).cuda()
+    dw1 = torch.from_numpy(w1.astype(np.uint32).view(np.int32)).cuda()
+    u0 = (w0.astype(np.float64) + 0.5) * 2.0 ** -32
+    x = (w1.astype(np.float64) + 0.5) * 2.0 ** -31                # angle / pi in (0, 2)
+    q = np.rint(2 * x)
+    xr = x - q / 2                                                # exact reduction, as the kernel's integer one
+    sn, cs = np.sin(np.pi * xr), np.cos(np.pi * xr)
+    k = q.astype(np.int64) % 4
+    s_ref = np.choose(k, [sn, cs, -sn, -cs])
+    c_ref = np.choose(k, [cs, -sn, -cs, sn])
+    rad = np.sqrt(-2 * np.log(u0))
+    # fp32 evaluation: (k + 1/2) 2^-24 rounds to 1.0 for the top words, so the radius is only good to ~4e-4 there
+    for f32, tol in ((0, 1e-14), (1, 1e-3)):
+        z0 = torch.empty(n, dtype=torch.float64, device="cuda")
+        z1 = torch.empty_like(z0)
+        nat.check(nat.lib().pcg_normal_pairs(dw0.data_ptr(), dw1.data_ptr(), z0.data_ptr(), z1.data_ptr(), n, f32,
+                                             torch.cuda.current_stream().cuda_stream))
+        torch.cuda.synchronize()
+        if f32:                                                   # 24-bit uniforms: compare on the truncated words
+            u0f = ((w0 >> np.uint64(8)).astype(np.float64) + 0.5) * 2.0 ** -24
+            u1f = ((w1 >> np.uint64(8)).astype(np.float64) + 0.5) * 2.0 ** -24
+            radf = np.sqrt(-2 * np.log(u0f))
+            ref0, ref1 = radf * np.cos(2 * np.pi * u1f), radf * np.sin(2 * np.pi * u1f)
+        else:
+            ref0, ref1 = rad * c_ref, rad * s_ref
+        scale = np.maximum(1.0, rad)
+        assert np.max(np.abs(z0.cpu().numpy() - ref0) / scale) < tol
+        assert np.max(np.abs(z1.cpu().numpy() - ref1) / scale) < tol
 
 
 @pytest.mark.parametrize("mode", ["philox", "philox_f32"])
