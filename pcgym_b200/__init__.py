@@ -11,9 +11,11 @@ include/pcgym_b200.h); importing this package without the built library raises.
 """
 from . import _native
 from .env import make_env
+from .evaluation_metrics import reproducibility_metric
 from .models import DeviceModel, model_mapping
+from .policy_evaluation import policy_eval
 
 _native.lib()   # no CPU fallback: fail at import time if the CUDA library is missing
 
-__all__ = ["make_env", "DeviceModel", "model_mapping"]
+__all__ = ["make_env", "reproducibility_metric", "policy_eval", "DeviceModel", "model_mapping"]
 __version__ = "0.1.0"

@@ -458,7 +458,7 @@ class make_env:
         nx = self.Nx_oracle
         z = lambda *s, dtype=f64: torch.zeros(*s, dtype=dtype, device=dev)
         self._x = z(nx, n)
-        self._x0_dev = torch.from_numpy(self._x0_host).to(dev)
+        self._x0_dev = torch.from_numpy(np.array(self._x0_host)).to(dev)
         self._sp_dev = torch.from_numpy(np.ascontiguousarray(self._sp_host)).to(dev) if self._sp_host is not None else None
         self._d_dev = torch.from_numpy(np.ascontiguousarray(self._d_host)).to(dev) if self._d_host is not None else None
         self._a_save = z(self._a_lo.shape[0], n) if self.a_delta else None
@@ -751,6 +751,23 @@ class make_env:
     @property
     def rhs_evaluations(self):
         return self._n_rhs
+
+    # ------------------------------------------------------------------ pcgym.py:617-692
+    def get_rollouts(self, policies: dict, reps: int, oracle: bool = False, dist_reward: bool = False,
+                     MPC_params=False, cons_viol: bool = False, **kw):
+        """Closed-loop rollouts of `policies`, `reps` repetitions each (the repetitions are the env batch of one
+        `policy_eval`); returns (evaluator, data) like the reference."""
+        from .policy_evaluation import policy_eval
+        evaluator = policy_eval(make_env, policies, reps, self.env_params, oracle, MPC_params, **kw)
+        return evaluator, evaluator.get_rollouts()
+
+    def plot_rollout(self, policies: dict, reps: int, oracle: bool = False, dist_reward: bool = False,
+                     MPC_params=False, cons_viol: bool = False, save_fig: bool = False, **kw):
+        from .policy_evaluation import policy_eval
+        evaluator = policy_eval(make_env, policies, reps, self.env_params, oracle, MPC_params, cons_viol, save_fig, **kw)
+        data = evaluator.get_rollouts()
+        evaluator.plot_data(data, dist_reward)              # raises: plotting is out of scope (DESIGN.md section 9)
+        return evaluator, data
 
     def close(self):
         self._bufs = {}
