@@ -30,9 +30,9 @@
 extern "C" {
 #endif
 
-#define PCG_ABI_VERSION 1
+#define PCG_ABI_VERSION 2
 
-#define PCG_MAX_NX    16   /* model states (biofilm_reactor)                    */
+#define PCG_MAX_NX    24   /* model states (heat_exchanger)                     */
 #define PCG_MAX_NU     8   /* manipulated inputs + model disturbance channels   */
 #define PCG_MAX_NSP    4   /* setpoint keys                                     */
 #define PCG_MAX_ND     4   /* model disturbance channels                        */
@@ -49,7 +49,20 @@ enum pcg_model {
   PCG_MODEL_FOUR_TANK = 3,        /* "four_tank"              model_classes.py:864  */
   PCG_MODEL_CRYSTALLIZATION = 4,  /* "crystallization"        model_classes.py:1232 */
   PCG_MODEL_BIOFILM = 5,          /* "biofilm_reactor"        model_classes.py:1046 */
-  PCG_MODEL_COUNT = 6
+  PCG_MODEL_COMPLEX_CSTR = 6,     /* "complex_cstr"           model_classes.py:65   */
+  PCG_MODEL_NONSMOOTH = 7,        /* "nonsmooth_control"      model_classes.py:509  */
+  PCG_MODEL_CSTR_SERIES = 8,      /* "cstr_series_recycle"    model_classes.py:611  */
+  PCG_MODEL_DISTILLATION = 9,     /* "distillation_column"    model_classes.py:682  */
+  PCG_MODEL_EXTRACTION_REACTIVE = 10, /* "multistage_extraction_reactive" model_classes.py:763 */
+  PCG_MODEL_HEAT_EXCHANGER = 11,  /* "heat_exchanger"         model_classes.py:935  */
+  PCG_MODEL_POLYMERISATION = 12,  /* "polymerisation_reactor" model_classes.py:1158 */
+  PCG_MODEL_PHOTO = 13,           /* "photobioreactor"        model_classes.py:433  */
+  PCG_MODEL_INVARIANT_BATCH = 14, /* "invariant_batch"        model_classes.py:268 (no inputs: 1 ignored input row) */
+  PCG_MODEL_BATCH = 15,           /* "batch"                  model_classes.py:222  */
+  PCG_MODEL_OSCILLATORS = 16,     /* "coupled_oscillator"     model_classes.py:186 (N = 10; no inputs: 1 ignored row) */
+  PCG_MODEL_DISEASE = 17,         /* "disease"                model_classes.py:156  */
+  PCG_MODEL_HYDRAULIC_TANK = 18,  /* "hydraulic_tank"         model_classes.py:128  */
+  PCG_MODEL_COUNT = 19
 };
 
 /* integrator: replaces integrator.py:90-107 (CVODES) / :65-88 (diffrax Tsit5 + PID 1e-8) */
@@ -158,7 +171,7 @@ typedef struct pcg_desc {
   double con_gx[PCG_MAX_NCON][PCG_MAX_OBS];
   double con_gu[PCG_MAX_NCON][PCG_MAX_NU];
   double con_h[PCG_MAX_NCON];
-  uint32_t con_mask_x[PCG_MAX_NCON];  /* nonzero columns of con_gx */
+  uint64_t con_mask_x[PCG_MAX_NCON];  /* nonzero columns of con_gx */
   uint32_t con_mask_u[PCG_MAX_NCON];  /* nonzero columns of con_gu */
 
   /* PCG_REWARD_OCP */

@@ -11,8 +11,8 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libpcgym_b200.so")
 
-ABI_VERSION = 1
-MAX_NX, MAX_NU, MAX_NSP, MAX_ND, MAX_NTAIL, MAX_NCON, MAX_PARAM = 16, 8, 4, 4, 8, 8, 16
+ABI_VERSION = 2
+MAX_NX, MAX_NU, MAX_NSP, MAX_ND, MAX_NTAIL, MAX_NCON, MAX_PARAM = 24, 8, 4, 4, 8, 8, 16
 MAX_OBS = MAX_NX + MAX_NSP + MAX_ND + MAX_NTAIL
 
 MODEL_IDS = {
@@ -22,6 +22,19 @@ MODEL_IDS = {
     "four_tank": 3,
     "crystallization": 4,
     "biofilm_reactor": 5,
+    "complex_cstr": 6,
+    "nonsmooth_control": 7,
+    "cstr_series_recycle": 8,
+    "distillation_column": 9,
+    "multistage_extraction_reactive": 10,
+    "heat_exchanger": 11,
+    "polymerisation_reactor": 12,
+    "photobioreactor": 13,
+    "invariant_batch": 14,
+    "batch": 15,
+    "coupled_oscillator": 16,
+    "disease": 17,
+    "hydraulic_tank": 18,
 }
 SCHEMES = {"rk4": 0, "dopri5": 1, "rk45": 1, "tsit5": 2}
 NOISE = {"off": 0, "philox": 1, "external": 2, "philox_f32": 3}
@@ -57,7 +70,7 @@ class Desc(C.Structure):
         ("con_gx", (f64 * MAX_OBS) * MAX_NCON),
         ("con_gu", (f64 * MAX_NU) * MAX_NCON),
         ("con_h", f64 * MAX_NCON),
-        ("con_mask_x", u32 * MAX_NCON),
+        ("con_mask_x", u64 * MAX_NCON),
         ("con_mask_u", u32 * MAX_NCON),
         ("ocp_R", f64), ("ocp_inv_span", f64 * MAX_NSP), ("ocp_mode", i32), ("_pad3", i32),
     ]

@@ -29,6 +29,34 @@ const double kCrD[] = {0.923714966, -6754.878558, 0.92229965554, 1.341205945, 48
 const char* const kBfN[] = {"V", "Va", "Kla", "m", "eq_exponent", "O_air", "vm_1", "vm_2", "K1", "K2", "KO_1", "KO_2"};
 const double kBfD[] = {10.0, 15.0, 1.5, 0.5, 1.0, 300, 0.8, 1.0, 0.5, 0.1, 1.5, 0.5};
 
+// further registry models (models_ext.cuh)
+const char* const kCcN[] = {"q", "V", "rho", "C", "deltaHr1", "EA1_over_R", "k01", "deltaHr2", "EA2_over_R", "k02", "UA", "Ti", "Caf"};
+const double kCcD[] = {100, 100, 1000, 0.239, -5e4, 8750, 7.2e10, -3e4, 9000, 1.0e10, 5e4, 350, 1};
+const char* const kNsN[] = {"a_11", "a_12", "a_21", "a_22", "b_1", "b_2"};
+const double kNsD[] = {0, 1, -2, -3, 0, 1};
+const char* const kCsN[] = {"C_O", "T_O", "V1", "V2", "U1A1", "U2A2", "rho", "cp", "k", "E", "deltaH", "R"};
+const double kCsD[] = {97.35, 298, 1e-3, 2e-3, 0.461, 0.732, 1.05e3, 3.766, 3.118e5, 46.14, 58.41, 8.3145e-3};
+const char* const kDcN[] = {"D", "q", "alpha", "X_feed", "M0", "Mb", "M"};
+const double kDcD[] = {100.0, 1.0, 5.0, 0.2, 2000.0, 2000.0, 2000.0};
+const char* const kErN[] = {"Vl", "Vg", "m", "Kla", "k", "eq_exponent", "XA0", "YA6", "YB6", "YC6"};
+const double kErD[] = {5.0, 5.0, 1.0, 0.01, 0.1, 2.0, 2.00, 0.00, 2.00, 0.00};
+const char* const kHxN[] = {"Utm", "Usm", "L", "Dt", "Dm", "Ds", "cpt", "cpm", "cps", "rhot", "rhom", "rhos"};
+const double kHxD[] = {1.0, 1.0, 1.0, 1.0, 2.0, 3.0, 1.0, 1.0, 1.0, 1.0, 1.0, 1.0};
+const char* const kPoN[] = {"Ap", "Ad", "At", "Ep_over_R", "Ed_over_R", "Et_over_R", "f", "V", "deltaHp", "rho", "cp"};
+const double kPoD[] = {6e10, 4e10, 9e10, 7750, 8500, 8250, 0.5, 1.0, -3e4, 1200.0, 2.0};
+const char* const kPhN[] = {"u_m", "u_d", "Y_NX", "k_m", "k_d", "k_sq", "K_Nq", "k_iq", "k_s", "k_i", "k_N"};
+const double kPhD[] = {0.0572, 0.0, 504.5, 0.00016, 0.281, 23.51, 16.89, 800.0, 178.9, 447.1, 393.1};
+const char* const kIbN[] = {"k1f", "k1r", "k2f", "k2r"};
+const double kIbD[] = {55.0, 1.0, 2.0, 1.0};
+const char* const kBaN[] = {"k01", "k02", "EA1", "EA2", "R", "dH1", "dH2", "rho", "Cp", "UA", "V"};
+const double kBaD[] = {1.0, 0.5, 5000, 6000, 8.314, -1000, -1500, 1000, 4.0, 100, 1.0};
+const char* const kOsN[] = {"N", "k", "m"};
+const double kOsD[] = {10, 1.0, 1.0};
+const char* const kDiN[] = {"beta", "gamma"};
+const double kDiD[] = {0.3, 0.1};
+const char* const kHtN[] = {"D"};
+const double kHtD[] = {1.0};
+
 template <class M>
 constexpr ModelInfo info(const char* const* n, const double* dflt, pcg::launch_fn f) {
   return ModelInfo{M::NX, M::NU, M::ND, M::NP, n, dflt, f};
@@ -41,6 +69,19 @@ const ModelInfo kModels[PCG_MODEL_COUNT] = {
     info<pcg::FourTank>(kFtN, kFtD, pcg::launch_four_tank),
     info<pcg::Crystallization>(kCrN, kCrD, pcg::launch_crystallization),
     info<pcg::Biofilm>(kBfN, kBfD, pcg::launch_biofilm),
+    info<pcg::ComplexCstr>(kCcN, kCcD, pcg::launch_complex_cstr),
+    info<pcg::Nonsmooth>(kNsN, kNsD, pcg::launch_nonsmooth),
+    info<pcg::CstrSeries>(kCsN, kCsD, pcg::launch_cstr_series),
+    info<pcg::Distillation>(kDcN, kDcD, pcg::launch_distillation),
+    info<pcg::ExtractionReactive>(kErN, kErD, pcg::launch_extraction_reactive),
+    info<pcg::HeatExchanger>(kHxN, kHxD, pcg::launch_heat_exchanger),
+    info<pcg::Polymerisation>(kPoN, kPoD, pcg::launch_polymerisation),
+    info<pcg::PhotoProduction>(kPhN, kPhD, pcg::launch_photo),
+    info<pcg::InvariantBatch>(kIbN, kIbD, pcg::launch_invariant_batch),
+    info<pcg::BatchReactor>(kBaN, kBaD, pcg::launch_batch),
+    info<pcg::Oscillators>(kOsN, kOsD, pcg::launch_oscillators),
+    info<pcg::Disease>(kDiN, kDiD, pcg::launch_disease),
+    info<pcg::HydraulicTank>(kHtN, kHtD, pcg::launch_hydraulic_tank),
 };
 
 // the measurement-noise transform on caller-supplied Philox words (pcg_normal_pairs)
@@ -69,6 +110,7 @@ int validate(const pcg_desc* d, const pcg_io* io, int64_t n_env, int64_t t0, int
   if (adaptive && d->scheme == PCG_SCHEME_RK4) return PCG_E_SCHEME;
   const ModelInfo& m = kModels[d->model];
   if (d->nu_a != m.nu) return PCG_E_DIMS;
+  if (d->model == PCG_MODEL_OSCILLATORS && d->theta[0] != pcg::Oscillators::NOSC) return PCG_E_DIMS;   // state count is 2 N
   if (d->nd != 0 && d->nd != m.nd) return PCG_E_DIMS;
   if (d->nsp < 0 || d->nsp > PCG_MAX_NSP || d->nd_obs < 0 || d->nd_obs > m.nd || d->n_tail < 0 ||
       d->n_tail > PCG_MAX_NTAIL || d->n_con < 0 || d->n_con > PCG_MAX_NCON)

@@ -148,7 +148,7 @@ template <class M, class TB, bool ADAPTIVE, bool GENERAL>
 cudaError_t launch_e(const pcg_desc& d, const pcg_io& io, int64_t n_env, int t0, int k_steps, cudaStream_t s) {
   // two envs per thread share one Philox block, which needs an even global id for the first of them
   const bool two = M::EPT == 2 && ept_override() != 1 && vector_ok(io, n_env) && d.env_id0 % 2 == 0;
-  if constexpr (!ADAPTIVE && !GENERAL) {
+  if constexpr (!ADAPTIVE && !GENERAL && M::FAST) {
     if (fast_ok<M>(d, io)) {
       if constexpr (M::EPT == 2) {
         if constexpr (M::WS > 0) {
@@ -197,5 +197,18 @@ cudaError_t launch_extraction(const pcg_desc&, const pcg_io&, int64_t, int, int,
 cudaError_t launch_four_tank(const pcg_desc&, const pcg_io&, int64_t, int, int, cudaStream_t);
 cudaError_t launch_crystallization(const pcg_desc&, const pcg_io&, int64_t, int, int, cudaStream_t);
 cudaError_t launch_biofilm(const pcg_desc&, const pcg_io&, int64_t, int, int, cudaStream_t);
+cudaError_t launch_complex_cstr(const pcg_desc&, const pcg_io&, int64_t, int, int, cudaStream_t);
+cudaError_t launch_nonsmooth(const pcg_desc&, const pcg_io&, int64_t, int, int, cudaStream_t);
+cudaError_t launch_cstr_series(const pcg_desc&, const pcg_io&, int64_t, int, int, cudaStream_t);
+cudaError_t launch_distillation(const pcg_desc&, const pcg_io&, int64_t, int, int, cudaStream_t);
+cudaError_t launch_extraction_reactive(const pcg_desc&, const pcg_io&, int64_t, int, int, cudaStream_t);
+cudaError_t launch_heat_exchanger(const pcg_desc&, const pcg_io&, int64_t, int, int, cudaStream_t);
+cudaError_t launch_polymerisation(const pcg_desc&, const pcg_io&, int64_t, int, int, cudaStream_t);
+cudaError_t launch_photo(const pcg_desc&, const pcg_io&, int64_t, int, int, cudaStream_t);
+cudaError_t launch_invariant_batch(const pcg_desc&, const pcg_io&, int64_t, int, int, cudaStream_t);
+cudaError_t launch_batch(const pcg_desc&, const pcg_io&, int64_t, int, int, cudaStream_t);
+cudaError_t launch_oscillators(const pcg_desc&, const pcg_io&, int64_t, int, int, cudaStream_t);
+cudaError_t launch_disease(const pcg_desc&, const pcg_io&, int64_t, int, int, cudaStream_t);
+cudaError_t launch_hydraulic_tank(const pcg_desc&, const pcg_io&, int64_t, int, int, cudaStream_t);
 
 }  // namespace pcg

@@ -48,6 +48,7 @@ struct Cstr {
   static constexpr int d_param[ND] = {8, 9};      // theta index of each disturbance default
   static constexpr int EPT = 2;                   // environments per thread (ILP 2 on the FP64 pipe)
   static constexpr int MIN_BLOCKS = 4, MIN_BLOCKS_EPT1 = 7;   // 7 x 64 threads x 144 regs: 65 536 envs in one wave
+  static constexpr bool FAST = true;              // has straight-line kernel instantiations (rollout_fast / rollout_ws)
   static constexpr int WS = 1;                    // warp-specialised kernel: integrator/finisher pairs per CTA
   using WsModel = struct CstrH;                   // RHS variant its integrator warps run
   PCG_DEV static void rhs(const P& p, const Aux& a, const double* x, const double*, double* dx) {
@@ -79,6 +80,7 @@ struct FirstOrder {
   PCG_DEV static void prep(const P&, const double*, Aux&) {}
   static constexpr int d_param[1] = {0};
   static constexpr int EPT = 2, MIN_BLOCKS = 8, MIN_BLOCKS_EPT1 = 8, WS = 0;
+  static constexpr bool FAST = true;
   PCG_DEV static void rhs(const P& p, const Aux&, const double* x, const double* u, double* dx) {
     dx[0] = fma(p.K, u[0], -x[0]) * p.inv_tau;                   // :322
   }
@@ -106,6 +108,7 @@ struct Extraction {
   PCG_DEV static void prep(const P&, const double*, Aux&) {}
   static constexpr int d_param[ND] = {5, 6};
   static constexpr int EPT = 1, MIN_BLOCKS = 4, MIN_BLOCKS_EPT1 = 4, WS = 0;
+  static constexpr bool FAST = true;
   PCG_DEV static void rhs(const P& p, const Aux&, const double* x, const double* u, double* dx) {
     const double L = u[0], G = u[1], X0 = u[2], Y6 = u[3];
 #pragma unroll
@@ -144,6 +147,7 @@ struct FourTank {
   PCG_DEV static void prep(const P&, const double*, Aux&) {}
   static constexpr int d_param[1] = {0};
   static constexpr int EPT = 1, MIN_BLOCKS = 4, MIN_BLOCKS_EPT1 = 4, WS = 0;
+  static constexpr bool FAST = true;
   PCG_DEV static void rhs(const P& p, const Aux&, const double* x, const double* u, double* dx) {
     const double s1 = sqrt(p.g2 * x[0]), s2 = sqrt(p.g2 * x[1]);   // NaN for h < 0, as the reference
     const double s3 = sqrt(p.g2 * x[2]), s4 = sqrt(p.g2 * x[3]);
@@ -168,6 +172,7 @@ struct Crystallization {
   PCG_DEV static void prep(const P&, const double*, Aux&) {}
   static constexpr int d_param[ND] = {0, 4, -1};   // "UA" is not a parameter of this model
   static constexpr int EPT = 1, MIN_BLOCKS = 4, MIN_BLOCKS_EPT1 = 4, WS = 0;
+  static constexpr bool FAST = true;
   PCG_DEV static void rhs(const P& p, const Aux&, const double* x, const double* u, double* dx) {
     const double mu0 = x[0], mu1 = x[1], mu2 = x[2], mu3 = x[3], conc = x[4];
     const double TK = u[0] + 273.15;
@@ -212,6 +217,7 @@ struct Biofilm {
   PCG_DEV static void prep(const P&, const double*, Aux&) {}
   static constexpr int d_param[1] = {0};
   static constexpr int EPT = 1, MIN_BLOCKS = 4, MIN_BLOCKS_EPT1 = 4, WS = 0;
+  static constexpr bool FAST = true;
   PCG_DEV static void rhs(const P& p, const Aux&, const double* x, const double* u, double* dx) {
     const double F = u[0], Fr = u[1];
     const double frv = Fr * p.inv_v, fra = Fr * p.inv_va, fa = F * p.inv_va;

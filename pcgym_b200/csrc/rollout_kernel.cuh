@@ -22,7 +22,7 @@
 #include <cstdint>
 
 #include "../../include/pcgym_b200.h"
-#include "models.cuh"
+#include "models_ext.cuh"
 #include "philox.cuh"
 #include "tableaus.cuh"
 
@@ -425,7 +425,7 @@ rollout_kernel(const __grid_constant__ pcg_desc d, const __grid_constant__ pcg_i
 #pragma unroll
             for (int e = 0; e < EPT; ++e) g[e] = fma(d.con_gu[c][i], uk[e][i], g[e]);
           if constexpr (GENERAL) {
-            const uint32_t mx = d.con_mask_x[c];
+            const uint64_t mx = d.con_mask_x[c];
             if (mx >> NX) {                           // rare: constraint reads SP / disturbance / tail slots
 #pragma unroll
               for (int e = 0; e < EPT; ++e) {

@@ -123,7 +123,8 @@ class make_env:
         # pcgym.py:160-165
         self.Nx_oracle = len(minfo["states"])
         self.Nx = self.Nx_oracle + (len(self.SP) if self.SP is not None else 0)
-        self.Nu = len(minfo["inputs"])
+        # input-less models (invariant_batch, coupled_oscillator) take one ignored action entry (csrc/models_ext.cuh)
+        self.Nu = max(len(minfo["inputs"]), 1)
         if n_a != self.Nu:
             raise ValueError(f"a_space has {n_a} entries but model '{self.model.name}' has {self.Nu} inputs")
 
@@ -134,11 +135,11 @@ class make_env:
             self.disturbance_active = True
             self.disturbances = P["disturbances"]
             self.Nd = len(self.disturbances)
-            self.Nd_model = len(minfo["disturbances"])
-            for k in minfo["disturbances"]:
+            self.Nd_model = len(minfo.get("disturbances") or [])
+            for k in (minfo.get("disturbances") or []):
                 if k not in self.disturbances and str(k) not in minfo["parameters"]:
                     raise KeyError(str(k))                                         # pcgym.py:400 on the reference
-            unknown = [k for k in self.disturbances if k not in minfo["disturbances"]]
+            unknown = [k for k in self.disturbances if k not in (minfo.get("disturbances") or [])]
             if unknown:
                 raise KeyError(f"disturbances {unknown} are not channels of model '{self.model.name}' "
                                f"({minfo['disturbances']})")
@@ -295,7 +296,7 @@ class make_env:
         else:
             self._sp_host = None
         # disturbances in model order (pcgym.py:392-405)
-        self._d_keys = [k for k in self.model.info()["disturbances"] if self.disturbance_active and k in self.disturbances]
+        self._d_keys = [k for k in (self.model.info().get("disturbances") or []) if self.disturbance_active and k in self.disturbances]
         ds = [self._per_time(self.disturbances[k], f"disturbances['{k}']") for k in self._d_keys]
         self._d_per_env = any(pe for _, pe in ds)
         if self._d_keys:
@@ -345,7 +346,7 @@ class make_env:
         nu_a = self._a_lo.shape[0]
         d.nu_a = nu_a
         params = self.model.info()["parameters"]
-        model_d = [] if self.model.disturbances in (["None"], []) else self.model.disturbances
+        model_d = [] if self.model.disturbances in (["None"], [], None) else self.model.disturbances
         d.nd = len(model_d) if self.disturbance_active else 0
         for i in range(nat.MAX_ND):
             d.d_src[i] = -1
@@ -632,7 +633,7 @@ class make_env:
         rows = [u]
         if self.disturbance_active:
             params = self.model.info()["parameters"]
-            for k in self.model.info()["disturbances"]:
+            for k in (self.model.info().get("disturbances") or []):
                 if k in self._d_keys:
                     j = self._d_keys.index(k)
                     v = self._d_dev[t_old + 1, j] if self._d_per_env else self._d_dev[j, t_old + 1].expand(self.n_envs)

@@ -21,10 +21,27 @@ _META = {
                         ["F", "Fr", "S1_F", "S2_F", "S3_F"], []),                          # :1138-1155
 }
 
-# registry keys of the reference that have no device RHS yet
-_NOT_YET = ["complex_cstr", "nonsmooth_control", "cstr_series_recycle", "distillation_column",
-            "multistage_extraction_reactive", "heat_exchanger", "polymerisation_reactor", "photobioreactor",
-            "invariant_batch", "batch", "coupled_oscillator", "disease", "hydraulic_tank"]
+# ---- further registry models (csrc/models_ext.cuh).  `info()["parameters"]` holds the numeric model parameters only
+# (the reference copies `self.__dict__`, which for some classes also carries "int_method" or the name lists);
+# kept from the reference: heat_exchanger has no "disturbances" key, photo_production adds "uncertainties": [].
+_META.update({
+    "complex_cstr": (["Ca", "Cb", "Cc", "T"], ["Tc"], ["Ti", "Caf"]),                        # :97-100
+    "nonsmooth_control": (["X1", "X2"], ["U"], ["None"]),                                   # :551-556
+    "cstr_series_recycle": (["C1", "T1", "C2", "T2"], ["F", "L", "Tc1", "Tc2"], []),        # :671-677
+    "distillation_column": (["X0", "X1", "X2", "X3", "Xf", "X4", "X5", "X6", "Xb"], ["R", "F"], []),   # :752-758
+    "multistage_extraction_reactive": ([f"{s}{k}" for k in range(1, 6) for s in ("XA", "YA", "YB", "YC")],
+                                       ["L", "G"], []),                                     # :853-859
+    "heat_exchanger": ([f"{s}{k}" for k in range(1, 9) for s in ("Tt", "Tm", "Ts")],
+                       ["Ft", "Fs", "Tt0", "Ts9"], None),                                   # :1036-1041 (no key)
+    "polymerisation_reactor": (["T", "M", "I"], ["F", "Tf", "Mf", "If"], []),               # :1222-1228
+    "photobioreactor": (["c_x", "c_N", "c_q"], ["I", "F_N"], []),                           # :497-505
+    "invariant_batch": (["xA", "xB", "xC", "xD"], [], []),                                  # :279-282
+    "batch": (["Ca", "Cb", "Cc", "T"], ["Tc"], []),                                         # :240-243
+    "coupled_oscillator": ([f"x{i + 1}" for i in range(10)] + [f"p{i + 1}" for i in range(10)], [], []),   # :197-200
+    "disease": (["S", "I", "R"], ["u"], []),                                                # :166-169
+    "hydraulic_tank": (["q1", "q2"], ["u"], []),                                            # :136-139
+})
+_NOT_YET = []
 
 
 class DeviceModel:
@@ -36,7 +53,7 @@ class DeviceModel:
         self.name = name
         self.model_id = _native.MODEL_IDS[name]
         self.int_method = int_method
-        self.states, self.inputs, self.disturbances = (list(v) for v in _META[name])
+        self.states, self.inputs, self.disturbances = (None if v is None else list(v) for v in _META[name])
         params = _native.model_params(self.model_id)
         for k, v in overrides.items():
             if k not in params:
@@ -44,8 +61,11 @@ class DeviceModel:
             params[k] = float(v)
         self.__dict__["_params"] = params
         nx, nu, nd, _ = _native.model_dims(self.model_id)
-        real_nd = 0 if self.disturbances in (["None"], []) else len(self.disturbances)
-        assert (nx, nu, nd) == (len(self.states), len(self.inputs), real_nd), "registry / library mismatch"
+        real_nd = 0 if self.disturbances in (["None"], [], None) else len(self.disturbances)
+        # input-less models carry one ignored input row on the device (csrc/models_ext.cuh)
+        assert (nx, nu, nd) == (len(self.states), max(len(self.inputs), 1), real_nd), "registry / library mismatch"
+        if name == "coupled_oscillator" and int(params["N"]) != 10:
+            raise NotImplementedError("coupled_oscillator: the state count is 2 N and only N = 10 has a device kernel")
 
     def __getattr__(self, k):
         p = self.__dict__.get("_params", {})
@@ -64,8 +84,12 @@ class DeviceModel:
         return list(self._params.values())
 
     def info(self) -> dict:
-        return {"parameters": dict(self._params), "states": self.states, "inputs": self.inputs,
-                "disturbances": self.disturbances}
+        out = {"parameters": dict(self._params), "states": self.states, "inputs": self.inputs}
+        if self.disturbances is not None:
+            out["disturbances"] = self.disturbances
+        if self.name == "photobioreactor":
+            out["uncertainties"] = []
+        return out
 
     def __call__(self, x, u):
         raise NotImplementedError(

@@ -18,7 +18,7 @@ What is substituted, because CasADi / SUNDIALS cannot be installed here:
     zero-order-hold contract as integrator.py:90-107).
 
 Outputs
-  rhs_vectors.npz        reference RHS at random points, 6 models (+ disturbance variants)
+  rhs_vectors.npz        reference RHS at random points, all 19 registry models (+ disturbance variants)
   traj_<model>.npz       golden do-mpc trajectories shipped by the reference
                          (pc-gym_paper/train_policies/*/data.npy -> ['oracle']['x','u'], rep 0)
   step_<case>.npz        per-step outputs of the reference make_env for tests/cases.py
@@ -125,20 +125,40 @@ def gen_rhs(mc, out):
         "biofilm_reactor": ([0.1, 0.1, 0.1, 0.1] * 4, [10, 10, 10, 400] * 4, [0, 1, .05, .05, .05], [10, 30, 1, 1, 1]),
         "crystallization": ([1e3, 2e4, 1e6, 2e8, 0.14, 0.1, 10], [2e3, 4e4, 3e6, 4e8, 0.17, 1.5, 20], [10], [40]),
     }
+    # further registry models, appended so the draws of the six above are unchanged.
+    # Input-less models get one ignored input column (the device kernels carry one, csrc/models_ext.cuh).
+    boxes.update({
+        "complex_cstr": ([0.3, 0.0, 0.0, 300], [1.0, 0.8, 0.5, 400], [290], [305], [340, 0.9], [360, 1.1]),
+        "nonsmooth_control": ([-2, -2], [2, 2], [-1], [1]),
+        "cstr_series_recycle": ([20, 290, 20, 290], [100, 340, 100, 340], [1e-6, 1e-6, 280, 280], [1e-4, 1e-4, 320, 320]),
+        "distillation_column": ([0.02] * 9, [0.98] * 9, [1, 150], [6, 400]),
+        "multistage_extraction_reactive": ([0.05] * 20, [2.0] * 20, [5, 10], [500, 1000]),
+        "heat_exchanger": ([280] * 24, [400] * 24, [0.5, 0.5, 350, 280], [5, 5, 400, 320]),
+        "polymerisation_reactor": ([300, 0.5, 0.01], [400, 6.0, 0.6], [0.01, 300, 1, 0.1], [1.0, 350, 8, 1.0]),
+        "photobioreactor": ([0.1, 50, 0.0], [5, 800, 0.3], [120, 0], [400, 40]),
+        "invariant_batch": ([0.0] * 4, [1.0] * 4, [0], [1]),
+        "batch": ([0.0, 0.0, 0.0, 280], [2.0, 1.5, 1.0, 400], [280], [350]),
+        "coupled_oscillator": ([-1] * 20, [1] * 20, [0], [1]),
+        "disease": ([0.0] * 3, [1.0] * 3, [0], [0.2]),
+        "hydraulic_tank": ([0.0, 0.0], [2.0, 2.0], [-1], [1]),
+    })
+    ref_class = {"photobioreactor": "photo_production", "coupled_oscillator": "coupled_oscillators",
+                 "disease": "disease_model"}
     data = {}
     M = 64
     for name, b in boxes.items():
-        model = getattr(mc, name)(int_method="casadi")
+        cls = getattr(mc, ref_class.get(name, name))
+        model = cls(int_method="casadi")
         x = rng.uniform(b[0], b[1], (M, len(b[0])))
         u = rng.uniform(b[2], b[3], (M, len(b[2])))
         data[f"{name}.x"], data[f"{name}.u"] = x, u
-        data[f"{name}.dx"] = np.stack([model(x[i], u[i]) for i in range(M)])
+        data[f"{name}.dx"] = np.stack([np.asarray(model(x[i], u[i]), float).reshape(-1) for i in range(M)])
+        assert data[f"{name}.dx"].shape == x.shape, name
         if len(b) == 6:
             d = rng.uniform(b[4], b[5], (M, len(b[4])))
             ud = np.concatenate([u, d], axis=1)
             data[f"{name}.ud"] = ud
-            data[f"{name}.dx_d"] = np.stack(
-                [getattr(mc, name)(int_method="casadi")(x[i], ud[i]) for i in range(M)])
+            data[f"{name}.dx_d"] = np.stack([cls(int_method="casadi")(x[i], ud[i]) for i in range(M)])
     np.savez_compressed(out, **data)
     print("wrote", out, len(data), "arrays")
 

@@ -99,8 +99,10 @@ def test_errors_like_reference():
         make_env([1, 2])
     with pytest.raises(ValueError):
         make_env(dict(cases.first_order(), model="nope"))
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(ValueError):                      # a_space length must match the model's inputs
         make_env(dict(cases.first_order(), model="heat_exchanger"))
+    with pytest.raises(NotImplementedError):             # custom Python RHS cannot run in the kernel
+        make_env(dict(cases.first_order(), custom_model=object()))
     with pytest.raises(KeyError):                        # four_tank's only disturbance key is "None" (pcgym.py:400)
         make_env(dict(cases.four_tank(), disturbances={"q1": np.ones(24)},
                       disturbance_bounds={"low": np.array([0.0]), "high": np.array([2.0])}))
@@ -160,3 +162,26 @@ def test_box_constraint_dict_descriptor():
         make_env(dict(p, cons_type=None))
     with pytest.raises(ValueError):
         make_env(dict(p, constraints={"Q": [1.0]}, cons_type={"Q": ["<="]}))
+
+
+def test_every_registry_key_of_the_reference_constructs():
+    """src/pcgym/pcgym.py:128-148: all 19 keys resolve to a device model whose dimensions the library confirms."""
+    from oracle import rhs as orhs
+    from pcgym_b200 import models
+    assert sorted(models.model_mapping()) == sorted(orhs.MODELS) and len(orhs.MODELS) == 19
+    for name, meta in orhs.MODELS.items():
+        m = models.get(name)
+        info = m.info()
+        assert info["states"] == meta["states"] and info["inputs"] == meta["inputs"], name
+        assert {k: float(v) for k, v in info["parameters"].items()} == {k: float(v) for k, v in meta["params"].items()}, name
+        nx, nu, nd, npar = nat.model_dims(m.model_id)
+        assert (nx, nu, npar) == (len(meta["states"]), max(len(meta["inputs"]), 1), len(meta["params"])), name
+    assert "disturbances" not in models.get("heat_exchanger").info()           # model_classes.py:1036-1041
+    assert models.get("photobioreactor").info()["uncertainties"] == []         # model_classes.py:497-505
+    env = make_env({"model": "heat_exchanger", "N": 10, "tsim": 5.0, "SP": {"Tt8": [350.0] * 10},
+                    "x0": np.array([360.0, 340.0, 320.0] * 8 + [350.0]),
+                    "o_space": {"low": np.full(25, 250.0), "high": np.full(25, 450.0)},
+                    "a_space": {"low": np.array([0.5, 0.5, 350.0, 280.0]), "high": np.array([5.0, 5.0, 400.0, 320.0])}})
+    assert (env.Nx_oracle, env.Nx, env.Nu) == (24, 25, 4) and env._desc.model == 11
+    with pytest.raises(NotImplementedError):
+        models.DeviceModel("coupled_oscillator", N=12)

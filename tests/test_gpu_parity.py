@@ -121,7 +121,24 @@ BATCH = {
     "multistage_extraction": dict(x0=[0.55, 0.3, 0.45, 0.25, 0.4, 0.20, 0.35, 0.15, 0.25, 0.1], a=([5.0, 10.0], [500.0, 1000.0]), dt=1.0, jitter=0.05),
     "crystallization": dict(x0=[1478.00986666666, 22995.8230590611, 1800863.24079725, 248516167.940593, 0.15861523304, 0.5, 15.0], a=([30.0], [40.0]), dt=1.0, jitter=0.01),   # T < 25 C blows the moments up
     "biofilm_reactor": dict(x0=[11.0, 5.3, 3.7, 480.0] * 4, a=([0, 1, 0.05, 0.05, 0.05], [10, 30, 1, 1, 1]), dt=2.0, jitter=0.02),
+    # further registry models; input-less models take one ignored action entry
+    "complex_cstr": dict(x0=[0.8, 0.1, 0.05, 330.0], a=([295.0], [302.0]), dt=0.25, jitter=0.02),
+    "nonsmooth_control": dict(x0=[1.0, 0.5], a=([-1.0], [1.0]), dt=0.1, jitter=0.5),
+    "cstr_series_recycle": dict(x0=[60.0, 310.0, 50.0, 310.0], a=([1e-5, 1e-5, 290.0, 290.0], [5e-5, 5e-5, 310.0, 310.0]), dt=5.0, jitter=0.02),
+    "distillation_column": dict(x0=list(np.linspace(0.9, 0.05, 9)), a=([1.0, 150.0], [5.0, 300.0]), dt=0.5, jitter=0.05),
+    "multistage_extraction_reactive": dict(x0=[1.0, 0.3, 1.5, 0.2] * 5, a=([5.0, 10.0], [500.0, 1000.0]), dt=0.02, jitter=0.05),
+    "heat_exchanger": dict(x0=[360.0, 340.0, 320.0] * 8, a=([0.5, 0.5, 350.0, 280.0], [5.0, 5.0, 400.0, 320.0]), dt=0.5, jitter=0.02),
+    "polymerisation_reactor": dict(x0=[330.0, 4.0, 0.3], a=([0.01, 300.0, 1.0, 0.1], [1.0, 350.0, 8.0, 1.0]), dt=0.05, jitter=0.01),
+    "photobioreactor": dict(x0=[1.0, 150.0, 0.01], a=([120.0, 0.0], [400.0, 40.0]), dt=1.0, jitter=0.05),
+    "invariant_batch": dict(x0=[1.0, 0.8, 0.1, 0.05], a=([0.0], [1.0]), dt=0.01, jitter=0.1),
+    "batch": dict(x0=[1.0, 0.2, 0.05, 320.0], a=([280.0], [350.0]), dt=0.5, jitter=0.02),
+    "coupled_oscillator": dict(x0=[0.5 + 0.3 * np.sin(i) for i in range(20)], a=([0.0], [1.0]), dt=0.1, jitter=0.1),
+    "disease": dict(x0=[0.9, 0.1, 0.05], a=([0.0], [0.2]), dt=1.0, jitter=0.05),
+    "hydraulic_tank": dict(x0=[1.0, 0.5], a=([-1.0], [1.0]), dt=0.1, jitter=0.2),
 }
+EXT_MODELS = ["complex_cstr", "nonsmooth_control", "cstr_series_recycle", "distillation_column",
+              "multistage_extraction_reactive", "heat_exchanger", "polymerisation_reactor", "photobioreactor",
+              "invariant_batch", "batch", "coupled_oscillator", "disease", "hydraulic_tank"]
 
 
 def batch_setup(model, n, K, seed=0):
@@ -173,6 +190,12 @@ def oracle_batch(model, params, x0, acts, key, sp, n_sub):
     ("crystallization", 1024, {"scheme": "tsit5", "adaptive": True, "rtol": 1e-9, "atol": 1e-12}, 1e-6),
     ("biofilm_reactor", 1024, {"scheme": "dopri5", "adaptive": True, "rtol": 1e-9, "atol": 1e-10}, 1e-6),
     ("cstr", 32, {"scheme": "rk4", "n_sub": 16}, 1e-8),
+] + [(m, 64, TIGHT, 1e-7 if m == "nonsmooth_control" else 1e-8)      # x2 crosses zero: relative error is loose there
+     for m in EXT_MODELS if m != "multistage_extraction_reactive"] + [
+    ("multistage_extraction_reactive", 512, dict(TIGHT, n_sub=200), 1e-7),      # fast gas-phase transients, tiny YC
+    ("complex_cstr", 64, {"scheme": "tsit5", "adaptive": True, "rtol": 1e-8, "atol": 1e-8}, 1e-6),
+    ("heat_exchanger", 64, {"scheme": "dopri5", "adaptive": True, "rtol": 1e-8, "atol": 1e-8}, 1e-6),
+    ("multistage_extraction_reactive", 512, {"scheme": "tsit5", "adaptive": True, "rtol": 1e-9, "atol": 1e-13}, 1e-6),
 ])
 def test_batch_rollout_vs_oracle(model, n_sub_oracle, integ, tol):
     n, K = (2048 if n_sub_oracle <= 256 else 192), 12
