@@ -205,6 +205,10 @@ typedef struct pcg_io {
   double* h_carry;         /* in/out [n] adaptive step size carried between intervals, or NULL */
   int32_t* n_rhs;          /* in/out [n] accumulated RHS evaluations, or NULL                  */
   double* u_prev;          /* in/out [nu_a][n] previous physical action (PCG_REWARD_OCP), or NULL */
+  const double* theta;     /* in     [nparam][n] per-environment model parameters (pcg_model_param_name order), or NULL
+                                     = desc.theta for every env.  Extension over the reference, where sampled
+                                     parameters never reach the dynamics (pcgym.py:301-316 vs integrator.py:28).
+                                     Disturbance channels that are not supplied fall back to the env's own theta. */
 } pcg_io;
 
 /* ABI version of the loaded library. */

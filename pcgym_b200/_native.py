@@ -86,7 +86,7 @@ class IO(C.Structure):
         ("x_traj", C.c_void_p), ("obs", C.c_void_p), ("reward", C.c_void_p),
         ("done", C.c_void_p), ("violated", C.c_void_p), ("g", C.c_void_p), ("g0", C.c_void_p),
         ("done_state", C.c_void_p), ("status", C.c_void_p), ("h_carry", C.c_void_p), ("n_rhs", C.c_void_p),
-        ("u_prev", C.c_void_p),
+        ("u_prev", C.c_void_p), ("theta", C.c_void_p),
     ]
 
 

@@ -138,7 +138,7 @@ int validate(const pcg_desc* d, const pcg_io* io, int64_t n_env, int64_t t0, int
   if (d->reward < 0 || d->reward > PCG_REWARD_OCP) return PCG_E_RANGE;
   if (d->reward == PCG_REWARD_OCP && d->ocp_mode != 0 && !io->u_prev) return PCG_E_NULL;
   const void* ptrs[] = {io->x, io->a, io->a_save, io->z, io->tail, io->x_traj, io->obs, io->reward, io->g, io->g0,
-                        io->h_carry, io->u_prev};
+                        io->h_carry, io->u_prev, io->theta};
   for (const void* p : ptrs)
     if (p && !aligned8(p)) return PCG_E_ALIGN;
   return PCG_OK;

@@ -19,7 +19,7 @@ inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) 
 // 128-bit row access needs an even env count (every row then starts 16-byte aligned) and aligned bases
 inline bool vector_ok(const pcg_io& io, int64_t n) {
   if (n % 2) return false;
-  const void* f64[] = {io.x, io.a, io.a_save, io.z, io.tail, io.x_traj, io.obs, io.reward, io.g, io.g0, io.u_prev};
+  const void* f64[] = {io.x, io.a, io.a_save, io.z, io.tail, io.x_traj, io.obs, io.reward, io.g, io.g0, io.u_prev, io.theta};
   for (const void* p : f64)
     if (!al16(p)) return false;
   return (reinterpret_cast<uintptr_t>(io.done) & 1u) == 0 && (reinterpret_cast<uintptr_t>(io.violated) & 1u) == 0;
@@ -170,7 +170,7 @@ cudaError_t launch_e(const pcg_desc& d, const pcg_io& io, int64_t n_env, int t0,
 
 template <class M, class TB, bool ADAPTIVE>
 cudaError_t launch_g(const pcg_desc& d, const pcg_io& io, int64_t n_env, int t0, int k_steps, cudaStream_t s) {
-  return needs_general<M>(d) ? launch_e<M, TB, ADAPTIVE, true>(d, io, n_env, t0, k_steps, s)
+  return (needs_general<M>(d) || io.theta != nullptr) ? launch_e<M, TB, ADAPTIVE, true>(d, io, n_env, t0, k_steps, s)
                              : launch_e<M, TB, ADAPTIVE, false>(d, io, n_env, t0, k_steps, s);
 }
 

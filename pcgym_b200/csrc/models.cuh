@@ -45,7 +45,7 @@ struct Cstr {
     a.feed_c = p.thru * u[2];                             // q/V Caf
     a.heat0 = fma(p.thru, u[1], p.c_cool * u[0]);         // q/V Ti + UA/(rho C V) Tc
   }
-  static constexpr int d_param[ND] = {8, 9};      // theta index of each disturbance default
+  PCG_HD static constexpr int dpar(int i) { constexpr int t[] = {8, 9}; return t[i]; }      // theta index of each disturbance default
   static constexpr int EPT = 2;                   // environments per thread (ILP 2 on the FP64 pipe)
   static constexpr int MIN_BLOCKS = 4, MIN_BLOCKS_EPT1 = 7;   // 7 x 64 threads x 144 regs: 65 536 envs in one wave
   static constexpr bool FAST = true;              // has straight-line kernel instantiations (rollout_fast / rollout_ws)
@@ -78,7 +78,7 @@ struct FirstOrder {
   PCG_HD static P make(const double* th) { return P{th[0], 1.0 / th[1]}; }
   struct Aux {};
   PCG_DEV static void prep(const P&, const double*, Aux&) {}
-  static constexpr int d_param[1] = {0};
+  PCG_HD static constexpr int dpar(int i) { constexpr int t[] = {0}; return t[i]; }
   static constexpr int EPT = 2, MIN_BLOCKS = 8, MIN_BLOCKS_EPT1 = 8, WS = 0;
   static constexpr bool FAST = true;
   PCG_DEV static void rhs(const P& p, const Aux&, const double* x, const double* u, double* dx) {
@@ -106,7 +106,7 @@ struct Extraction {
   }
   struct Aux {};
   PCG_DEV static void prep(const P&, const double*, Aux&) {}
-  static constexpr int d_param[ND] = {5, 6};
+  PCG_HD static constexpr int dpar(int i) { constexpr int t[] = {5, 6}; return t[i]; }
   static constexpr int EPT = 1, MIN_BLOCKS = 4, MIN_BLOCKS_EPT1 = 4, WS = 0;
   static constexpr bool FAST = true;
   PCG_DEV static void rhs(const P& p, const Aux&, const double* x, const double* u, double* dx) {
@@ -145,7 +145,7 @@ struct FourTank {
   }
   struct Aux {};
   PCG_DEV static void prep(const P&, const double*, Aux&) {}
-  static constexpr int d_param[1] = {0};
+  PCG_HD static constexpr int dpar(int i) { constexpr int t[] = {0}; return t[i]; }
   static constexpr int EPT = 1, MIN_BLOCKS = 4, MIN_BLOCKS_EPT1 = 4, WS = 0;
   static constexpr bool FAST = true;
   PCG_DEV static void rhs(const P& p, const Aux&, const double* x, const double* u, double* dx) {
@@ -170,7 +170,7 @@ struct Crystallization {
   }
   struct Aux {};
   PCG_DEV static void prep(const P&, const double*, Aux&) {}
-  static constexpr int d_param[ND] = {0, 4, -1};   // "UA" is not a parameter of this model
+  PCG_HD static constexpr int dpar(int i) { constexpr int t[] = {0, 4, -1}; return t[i]; }   // "UA" is not a parameter of this model
   static constexpr int EPT = 1, MIN_BLOCKS = 4, MIN_BLOCKS_EPT1 = 4, WS = 0;
   static constexpr bool FAST = true;
   PCG_DEV static void rhs(const P& p, const Aux&, const double* x, const double* u, double* dx) {
@@ -215,7 +215,7 @@ struct Biofilm {
   }
   struct Aux {};
   PCG_DEV static void prep(const P&, const double*, Aux&) {}
-  static constexpr int d_param[1] = {0};
+  PCG_HD static constexpr int dpar(int i) { constexpr int t[] = {0}; return t[i]; }
   static constexpr int EPT = 1, MIN_BLOCKS = 4, MIN_BLOCKS_EPT1 = 4, WS = 0;
   static constexpr bool FAST = true;
   PCG_DEV static void rhs(const P& p, const Aux&, const double* x, const double* u, double* dx) {

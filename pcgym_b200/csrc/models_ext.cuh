@@ -33,7 +33,7 @@ struct ComplexCstr {
     p.c_cool = th[10] / (th[2] * th[3] * th[1]);
     return p;
   }
-  static constexpr int d_param[ND] = {11, 12};
+  PCG_HD static constexpr int dpar(int i) { constexpr int t[] = {11, 12}; return t[i]; }
   PCG_EXT_TRAITS
   PCG_DEV static void rhs(const P& p, const Aux&, const double* x, const double* u, double* dx) {
     const double ca = x[0], cb = x[1], cc = x[2], T = x[3];
@@ -53,7 +53,7 @@ struct Nonsmooth {
   static constexpr int NX = 2, NU = 1, ND = 0, NP = 6;
   struct P { double a11, a12, a21, a22, b1, b2; };
   PCG_HD static P make(const double* th) { return P{th[0], th[1], th[2], th[3], th[4], th[5]}; }
-  static constexpr int d_param[1] = {0};
+  PCG_HD static constexpr int dpar(int i) { constexpr int t[] = {0}; return t[i]; }
   PCG_EXT_TRAITS
   PCG_DEV static void rhs(const P& p, const Aux&, const double* x, const double* u, double* dx) {
     dx[0] = fma(p.a11, x[0], fma(p.a12, x[1], p.b1 * u[0]));                    // :536
@@ -80,7 +80,7 @@ struct CstrSeries {
     p.neg_e_r = -th[9] / th[11];
     return p;
   }
-  static constexpr int d_param[1] = {0};
+  PCG_HD static constexpr int dpar(int i) { constexpr int t[] = {0}; return t[i]; }
   PCG_EXT_TRAITS
   PCG_DEV static void rhs(const P& p, const Aux&, const double* x, const double* u, double* dx) {
     const double C1 = x[0], T1 = x[1], C2 = x[2], T2 = x[3];
@@ -102,7 +102,7 @@ struct Distillation {
   PCG_HD static P make(const double* th) {
     return P{th[0], th[1], th[2], th[2] - 1.0, th[3], 1.0 / th[4], 1.0 / th[5], 1.0 / th[6]};
   }
-  static constexpr int d_param[1] = {0};
+  PCG_HD static constexpr int dpar(int i) { constexpr int t[] = {0}; return t[i]; }
   PCG_EXT_TRAITS
   PCG_DEV static void rhs(const P& p, const Aux&, const double* x, const double* u, double* dx) {
     const double R = u[0], F = u[1];
@@ -141,7 +141,7 @@ struct ExtractionReactive {
     p.xa0 = th[6];  p.ya6 = th[7];  p.yb6 = th[8];  p.yc6 = th[9];
     return p;
   }
-  static constexpr int d_param[1] = {0};
+  PCG_HD static constexpr int dpar(int i) { constexpr int t[] = {0}; return t[i]; }
   PCG_EXT_TRAITS
   PCG_DEV static void rhs(const P& p, const Aux&, const double* x, const double* u, double* dx) {
     const double L = u[0], G = u[1];
@@ -187,7 +187,7 @@ struct HeatExchanger {
     p.cps = th[8];
     return p;
   }
-  static constexpr int d_param[1] = {0};
+  PCG_HD static constexpr int dpar(int i) { constexpr int t[] = {0}; return t[i]; }
   PCG_EXT_TRAITS
   PCG_DEV static void rhs(const P& p, const Aux&, const double* x, const double* u, double* dx) {
     const double Ft = u[0], Fs = u[1], Tt0 = u[2], Ts9 = u[3];
@@ -214,7 +214,7 @@ struct Polymerisation {
     return P{log(th[0]), log(th[1]), log(th[2]), -th[3], -th[4], -th[5], th[6], 1.0 / th[7],
              (-th[8]) / (th[9] * th[10])};
   }
-  static constexpr int d_param[1] = {0};
+  PCG_HD static constexpr int dpar(int i) { constexpr int t[] = {0}; return t[i]; }
   PCG_EXT_TRAITS
   PCG_DEV static void rhs(const P& p, const Aux&, const double* x, const double* u, double* dx) {
     const double T = x[0], M = x[1], I = x[2];
@@ -240,7 +240,7 @@ struct PhotoProduction {
   PCG_HD static P make(const double* th) {
     return P{th[0], th[1], th[2], th[3], th[4], th[5], th[6], th[7], th[8], th[9], th[10]};
   }
-  static constexpr int d_param[1] = {0};
+  PCG_HD static constexpr int dpar(int i) { constexpr int t[] = {0}; return t[i]; }
   static constexpr int EPT = 1, MIN_BLOCKS = 4, MIN_BLOCKS_EPT1 = 4, WS = 0;
   static constexpr bool FAST = false;
   struct Aux { double gx, gq; };                 // light-limitation factors: functions of the held input only
@@ -264,7 +264,7 @@ struct InvariantBatch {
   static constexpr int NX = 4, NU = 1, ND = 0, NP = 4;
   struct P { double k1f, k1r, k2f, k2r; };
   PCG_HD static P make(const double* th) { return P{th[0], th[1], th[2], th[3]}; }
-  static constexpr int d_param[1] = {0};
+  PCG_HD static constexpr int dpar(int i) { constexpr int t[] = {0}; return t[i]; }
   PCG_EXT_TRAITS
   PCG_DEV static void rhs(const P& p, const Aux&, const double* x, const double*, double* dx) {
     const double q1 = p.k1f * x[0] * x[1] - p.k1r * x[2];
@@ -290,7 +290,7 @@ struct BatchReactor {
     p.cool = th[9] / (th[7] * th[8] * th[10]);
     return p;
   }
-  static constexpr int d_param[1] = {0};
+  PCG_HD static constexpr int dpar(int i) { constexpr int t[] = {0}; return t[i]; }
   PCG_EXT_TRAITS
   PCG_DEV static void rhs(const P& p, const Aux&, const double* x, const double* u, double* dx) {
     const double T = x[3];
@@ -312,7 +312,7 @@ struct Oscillators {
   static constexpr int NX = 2 * NOSC, NU = 1, ND = 0, NP = 3;
   struct P { double k, inv_m; };
   PCG_HD static P make(const double* th) { return P{th[1], 1.0 / th[2]}; }
-  static constexpr int d_param[1] = {0};
+  PCG_HD static constexpr int dpar(int i) { constexpr int t[] = {0}; return t[i]; }
   PCG_EXT_TRAITS
   PCG_DEV static void rhs(const P& p, const Aux&, const double* x, const double*, double* dx) {
 #pragma unroll
@@ -330,7 +330,7 @@ struct Disease {
   static constexpr int NX = 3, NU = 1, ND = 0, NP = 2;
   struct P { double beta, gamma; };
   PCG_HD static P make(const double* th) { return P{th[0], th[1]}; }
-  static constexpr int d_param[1] = {0};
+  PCG_HD static constexpr int dpar(int i) { constexpr int t[] = {0}; return t[i]; }
   PCG_EXT_TRAITS
   PCG_DEV static void rhs(const P& p, const Aux&, const double* x, const double* u, double* dx) {
     const double S = x[0], I = x[1], inf = p.beta * S * I, vac = u[0] * S;
@@ -346,7 +346,7 @@ struct HydraulicTank {
   static constexpr int NX = 2, NU = 1, ND = 0, NP = 1;
   struct P { double D; };
   PCG_HD static P make(const double* th) { return P{th[0]}; }
-  static constexpr int d_param[1] = {0};
+  PCG_HD static constexpr int dpar(int i) { constexpr int t[] = {0}; return t[i]; }
   PCG_EXT_TRAITS
   PCG_DEV static void rhs(const P& p, const Aux&, const double* x, const double* u, double* dx) {
     const double flow = p.D * (x[0] - x[1]);

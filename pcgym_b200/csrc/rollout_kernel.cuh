@@ -98,17 +98,25 @@ PCG_DEV void st_flags(uint8_t* p, const bool (&f)[EPT]) {
   }
 }
 
+// Model constants as seen by EPT environments: the same constant-bank block for all of them (UniformP), or a
+// per-environment copy built in registers from io.theta (an array of M::P).  Both index as pa[e].
+template <class P>
+struct UniformP {
+  const P& p;
+  PCG_DEV const P& operator[](int) const { return p; }
+};
+
 // ------------------------------------------------------------------ fixed step: n_sub steps of h = dt / n_sub
 // The EPT environments advance in lock step: their RHS evaluations sit in one basic block so the
 // scheduler interleaves the two dependency chains.
-template <class M, class TB, int EPT>
-PCG_DEV void rk_step_fixed(const Derived<M, TB>& dv, const typename M::Aux (&aux)[EPT], double (&x)[EPT][M::NX],
-                           const double (&u)[EPT][M::NU + M::ND]) {
+template <class M, class TB, int EPT, class PA>
+PCG_DEV void rk_step_fixed(const Derived<M, TB>& dv, const PA& pa, const typename M::Aux (&aux)[EPT],
+                           double (&x)[EPT][M::NX], const double (&u)[EPT][M::NU + M::ND]) {
   constexpr int NX = M::NX;
   {
     double k[TB::S][EPT][NX];
 #pragma unroll
-    for (int e = 0; e < EPT; ++e) M::rhs(dv.p, aux[e], x[e], u[e], k[0][e]);
+    for (int e = 0; e < EPT; ++e) M::rhs(pa[e], aux[e], x[e], u[e], k[0][e]);
 #pragma unroll
     for (int i = 1; i < TB::S; ++i) {
       double xi[EPT][NX];
@@ -123,7 +131,7 @@ PCG_DEV void rk_step_fixed(const Derived<M, TB>& dv, const typename M::Aux (&aux
           xi[e][n] = acc;
         }
 #pragma unroll
-      for (int e = 0; e < EPT; ++e) M::rhs(dv.p, aux[e], xi[e], u[e], k[i][e]);
+      for (int e = 0; e < EPT; ++e) M::rhs(pa[e], aux[e], xi[e], u[e], k[i][e]);
     }
 #pragma unroll
     for (int e = 0; e < EPT; ++e)
@@ -137,6 +145,11 @@ PCG_DEV void rk_step_fixed(const Derived<M, TB>& dv, const typename M::Aux (&aux
       }
   }
 }
+template <class M, class TB, int EPT>
+PCG_DEV void rk_step_fixed(const Derived<M, TB>& dv, const typename M::Aux (&aux)[EPT], double (&x)[EPT][M::NX],
+                           const double (&u)[EPT][M::NU + M::ND]) {
+  rk_step_fixed<M, TB, EPT>(dv, UniformP<typename M::P>{dv.p}, aux, x, u);
+}
 
 // ------------------------------------------------------------------ adaptive step, one environment
 // Embedded 5(4) pair, per-lane error control.  Controller as in Hairer/Norsett/Wanner II.4 (and scipy
@@ -145,16 +158,17 @@ PCG_DEV void rk_step_fixed(const Derived<M, TB>& dv, const typename M::Aux (&aux
 // different step counts; `max_steps` bounds the loop and a non-finite error estimate is treated as a
 // rejection so one bad lane cannot stall its warp.
 template <class M, class TB>
-PCG_DEV void advance_adaptive(const Derived<M, TB>& dv, double (&x)[M::NX], const double (&u)[M::NU + M::ND], double dt,
+PCG_DEV void advance_adaptive(const Derived<M, TB>& dv, const typename M::P& mp, double (&x)[M::NX],
+                              const double (&u)[M::NU + M::ND], double dt,
                               double rtol, double atol, int max_steps, double& h_carry, int& n_rhs,
                               unsigned& status) {
   constexpr int NX = M::NX, S = TB::S;
   double t = 0.0;
   double h = (h_carry > 0.0 && h_carry < dt) ? h_carry : dt;
   typename M::Aux aux;
-  M::prep(dv.p, u, aux);
+  M::prep(mp, u, aux);
   double k0[NX];
-  M::rhs(dv.p, aux, x, u, k0);
+  M::rhs(mp, aux, x, u, k0);
   ++n_rhs;
   int steps = 0;
   bool rejected = false;
@@ -179,7 +193,7 @@ PCG_DEV void advance_adaptive(const Derived<M, TB>& dv, double (&x)[M::NX], cons
           if (TB::a(i, j) != 0.0) acc = fma(dv.a[i][j], hk[j][n], acc);
         xi[n] = acc;
       }
-      M::rhs(dv.p, aux, xi, u, k);
+      M::rhs(mp, aux, xi, u, k);
 #pragma unroll
       for (int n = 0; n < NX; ++n) hk[i][n] = hh * k[n];
     }
@@ -192,7 +206,7 @@ PCG_DEV void advance_adaptive(const Derived<M, TB>& dv, double (&x)[M::NX], cons
         if (TB::b(i) != 0.0) acc = fma(dv.b[i], hk[i][n], acc);
       xn[n] = acc;
     }
-    M::rhs(dv.p, aux, xn, u, kn);                    // FSAL stage: k_{S+1} = f(x_new)
+    M::rhs(mp, aux, xn, u, kn);                      // FSAL stage: k_{S+1} = f(x_new)
     n_rhs += S;
     double sq = 0.0;
 #pragma unroll
@@ -291,6 +305,26 @@ rollout_kernel(const __grid_constant__ pcg_desc d, const __grid_constant__ pcg_i
     h_carry[e] = (ADAPTIVE && io.h_carry) ? io.h_carry[env0 + e] : 0.0;
   }
 
+  // ---- model constants: the descriptor's (constant bank) or, GENERAL only, built per env from io.theta
+  constexpr int NPL = GENERAL ? EPT : 1;
+  typename M::P p_env[NPL];
+  double d_def[NPL][ND > 0 ? ND : 1];          // what an unsupplied disturbance channel falls back to
+  const bool per_env = GENERAL && io.theta != nullptr;
+#pragma unroll
+  for (int e = 0; e < NPL; ++e) {
+    p_env[e] = dv.p;
+#pragma unroll
+    for (int i = 0; i < ND; ++i) d_def[e][i] = d.d_default[i];
+    if (per_env) {
+      double th[M::NP];
+#pragma unroll
+      for (int i = 0; i < M::NP; ++i) th[i] = io.theta[static_cast<int64_t>(i) * n + env0 + e];
+      p_env[e] = M::make(th);
+#pragma unroll
+      for (int i = 0; i < ND; ++i)
+        if (M::dpar(i) >= 0) d_def[e][i] = th[M::dpar(i)];
+    }
+  }
   const bool ocp = d.reward == PCG_REWARD_OCP;
   double u_prev[EPT][NU];
 #pragma unroll
@@ -384,7 +418,7 @@ rollout_kernel(const __grid_constant__ pcg_desc d, const __grid_constant__ pcg_i
       // ---- disturbances at t+1 (pcgym.py:386-412); defaults when inactive so the RHS needs no branch
 #pragma unroll
       for (int i = 0; i < ND; ++i) {
-        double v = d.d_default[i];
+        double v = GENERAL ? d_def[e][i] : d.d_default[i];
         if (dist_on && d.d_src[i] >= 0)
           v = io.dist[static_cast<int64_t>(t + 1) * io.d_st + d.d_src[i] * io.d_sj + (env0 + e) * io.d_se];
         uk[e][NU + i] = v;
@@ -501,16 +535,19 @@ rollout_kernel(const __grid_constant__ pcg_desc d, const __grid_constant__ pcg_i
       draw();
 #pragma unroll
       for (int e = 0; e < EPT; ++e)
-        advance_adaptive<M, TB>(dv, x[e], uk[e], d.dt, d.rtol, d.atol, d.max_steps, h_carry[e], n_rhs[e], status[e]);
+        advance_adaptive<M, TB>(dv, GENERAL ? p_env[e % NPL] : dv.p, x[e], uk[e], d.dt, d.rtol, d.atol, d.max_steps,
+                                h_carry[e], n_rhs[e], status[e]);
     } else {
       typename M::Aux aux[EPT];
 #pragma unroll
-      for (int e = 0; e < EPT; ++e) M::prep(dv.p, uk[e], aux[e]);
-      if (d.n_sub == 1) {
-        draw();
+      for (int e = 0; e < EPT; ++e) M::prep(GENERAL ? p_env[e % NPL] : dv.p, uk[e], aux[e]);
+      draw();
+      if constexpr (GENERAL) {
+#pragma unroll 1
+        for (int s = 0; s < d.n_sub; ++s) rk_step_fixed<M, TB, EPT>(dv, p_env, aux, x, uk);
+      } else if (d.n_sub == 1) {
         rk_step_fixed<M, TB, EPT>(dv, aux, x, uk);
       } else {
-        draw();
 #pragma unroll 1
         for (int s = 0; s < d.n_sub; ++s) rk_step_fixed<M, TB, EPT>(dv, aux, x, uk);
       }

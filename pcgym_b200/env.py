@@ -16,7 +16,10 @@ file parses the configuration into a `pcg_desc`, owns the device tensors (struct
 New optional keys: `n_envs`, `device`, `seed`, `env_id0`, `noise_mode` ("philox" | "philox_f32" |
 "external"), `integrator` = {"scheme": "tsit5"|"dopri5"|"rk4", "adaptive": bool, "rtol", "atol",
 "n_sub", "max_steps"}, `constraint_units` ("reference" | "physical"), per-env `x0` [n_envs, Nx],
-per-env `SP[k]` / `disturbances[k]` [n_envs, N].
+per-env `SP[k]` / `disturbances[k]` [n_envs, N]; per-env model parameters that reach the DYNAMICS (an
+extension: the reference's sampled parameters only reach the observation): `model_params` =
+{"k0": array[n_envs], ...} and/or `uncertainty_in_dynamics=True`, which feeds the values reset() samples for
+`uncertainty_percentages` / `empirical_distribution` to the kernel as well.
 """
 from __future__ import annotations
 
@@ -167,6 +170,18 @@ class make_env:
             self.NUn = len(names)
             o_lo = np.concatenate((o_lo, _np(P["uncertainty_bounds"]["low"]).ravel()))
             o_hi = np.concatenate((o_hi, _np(P["uncertainty_bounds"]["high"]).ravel()))
+        # extension: parameters that differ per env and DO reach the dynamics
+        self.uncertainty_in_dynamics = bool(P.get("uncertainty_in_dynamics", False)) and self.uncertainty
+        self._theta_names = list(self.model.info()["parameters"])
+        self._theta_user = {}
+        for k, v in (P.get("model_params") or {}).items():
+            if k not in self._theta_names:
+                raise AttributeError(f"{self.model.name} has no parameter {k!r}")
+            v = _np(v).reshape(-1)
+            if v.shape[0] not in (1, self.n_envs):
+                raise ValueError(f"model_params[{k!r}] must have n_envs = {self.n_envs} entries")
+            self._theta_user[k] = np.broadcast_to(v, (self.n_envs,)).copy()
+        self._per_env_theta = bool(self._theta_user) or self.uncertainty_in_dynamics
         self.observation_space_base = Box(o_lo, o_hi)
         n_o = o_lo.shape[0]
         self.observation_space = Box(-np.ones(n_o), np.ones(n_o)) if self.normalise_o else self.observation_space_base
@@ -471,6 +486,12 @@ class make_env:
         self._n_rhs = z(n, dtype=torch.int32)
         # cons_info lives as [N, n_con, n_envs] so the kernel writes rows in place; exposed as (n_con, N, n_envs)
         self._cons = z(self.N, max(self.n_con, 1), n) if self.n_con else None
+        self._theta = None
+        if self._per_env_theta:                      # [nparam, n]: defaults, then the user's per-env rows
+            base = torch.tensor([float(v) for v in self.model.info()["parameters"].values()], dtype=f64, device=dev)
+            self._theta = base[:, None].expand(-1, n).contiguous()
+            for k, v in self._theta_user.items():
+                self._theta[self._theta_names.index(k)] = torch.from_numpy(v).to(dev)
         self._bufs = {}
         self._a_step = z(1, self._a_lo.shape[0], n)
         self._o_lo = torch.from_numpy(self.observation_space_base.low.astype(np.float64)).to(dev)
@@ -512,6 +533,7 @@ class make_env:
             io.g = self._cons[self.t + 1].data_ptr() if self.t + 1 < self.N else None
         io.done_state, io.status, io.h_carry, io.n_rhs = p(self._done_state), p(self._status), p(self._h_carry), p(self._n_rhs)
         io.u_prev = p(self._u_prev)
+        io.theta = p(self._theta)
         return io
 
     # ------------------------------------------------------------------ reset (pcgym.py:263-349)
@@ -541,6 +563,9 @@ class make_env:
                     rows.append(vals[torch.randint(len(vals), (n,), generator=gen, device=self.device)])
             self._tail.copy_(torch.stack(rows))
             parts.append(self._tail)
+            if self.uncertainty_in_dynamics:         # the sampled values also drive the RHS of their env
+                for j, name in enumerate(self._unc_names):
+                    self._theta[self._theta_names.index(name)] = self._tail[j]
         if self.a_delta:
             self.a_save_init = _np(self.a_0).reshape(-1)
             self._a_save.copy_(torch.as_tensor(self.a_save_init, device=self.device)[:, None].expand(-1, n))

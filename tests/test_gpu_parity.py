@@ -415,6 +415,61 @@ def test_uncertainty_is_observation_only():
     assert rel(env._x.cpu().numpy(), x) < 1e-9
 
 
+def test_per_env_parameters_reach_the_dynamics():
+    """Row f4 (extension): `model_params` rows and, with uncertainty_in_dynamics, the sampled uncertain parameters
+    drive each env's own RHS; the oracle integrates the same RHS with per-env parameter arrays."""
+    n, K = 384, 10
+    rng = np.random.default_rng(9)
+    k0 = 7.2e10 * (1 + 0.03 * rng.uniform(-1, 1, n))       # larger spreads tip some envs into thermal runaway,
+    ua = 5e4 * (1 + 0.05 * rng.uniform(-1, 1, n))          # where no integrator agrees with another to 1e-9
+    p = cases.cstr_basic()
+    p.update(noise=False, model_params={"k0": k0, "UA": ua})
+    env = _env(p, n_envs=n, integrator=TIGHT)
+    env.reset()
+    acts = rng.uniform(-1, 1, (K, 1, n))
+    out = env.rollout(torch.as_tensor(acts))
+    par = orhs.default_params("cstr")
+    par.update(k0=k0, UA=ua)
+    x = np.tile(np.array([[0.8], [330.0]]), (1, n))
+    for k in range(K):
+        x = oint.advance_dense("cstr", x, (acts[k] + 1) * 3.5 + 295.0, 0.25, p=par, n_sub=32)
+        assert rel(out["x"][k].cpu().numpy(), x) < 1e-9, k
+    base = _env(dict(p, model_params=None), n_envs=n, integrator=TIGHT)
+    base.reset()
+    assert rel(base.rollout(torch.as_tensor(acts))["x"][-1].cpu().numpy(), x) > 1e-5      # the parameters mattered
+
+    # an unsupplied disturbance channel falls back to the env's OWN parameter (Caf), a supplied one (Ti) wins
+    caf = 1.0 + 0.05 * rng.uniform(-1, 1, n)
+    ti = np.repeat(rng.uniform(345, 355, p["N"] // 4), 4)
+    pd = cases.cstr_basic()
+    pd.update(noise=False, model_params={"Caf": caf, "Ti": np.full(n, 999.0)}, disturbances={"Ti": ti},
+              disturbance_bounds={"low": np.array([330.0]), "high": np.array([370.0])})
+    envd = _env(pd, n_envs=n, integrator=TIGHT)
+    envd.reset()
+    outd = envd.rollout(torch.as_tensor(acts))
+    x = np.tile(np.array([[0.8], [330.0]]), (1, n))
+    for k in range(K):
+        u = np.concatenate([(acts[k] + 1) * 3.5 + 295.0, np.full((1, n), ti[k + 1]), caf[None]])
+        x = oint.advance_dense("cstr", x, u, 0.25, n_sub=32)
+        assert rel(outd["x"][k].cpu().numpy(), x) < 1e-9, k
+
+    # uncertainty_in_dynamics: the k0 reset() samples (and shows in the observation) is the k0 the env integrates with
+    pu = cases.cstr_basic()
+    pu.update(noise=False, uncertainty_percentages={"k0": 0.03}, distribution="uniform", uncertainty_in_dynamics=True,
+              uncertainty_bounds={"low": np.array([6e10]), "high": np.array([8e10])})
+    envu = _env(pu, n_envs=n, integrator=TIGHT)
+    obs, _ = envu.reset()
+    k0s = (obs[:, 3].cpu().numpy() + 1) / 2 * 2e10 + 6e10
+    assert k0s.std() > 0
+    outu = envu.rollout(torch.as_tensor(acts))
+    par = orhs.default_params("cstr")
+    par.update(k0=k0s)
+    x = np.tile(np.array([[0.8], [330.0]]), (1, n))
+    for k in range(K):
+        x = oint.advance_dense("cstr", x, (acts[k] + 1) * 3.5 + 295.0, 0.25, p=par, n_sub=32)
+    assert rel(outu["x"][-1].cpu().numpy(), x) < 1e-8
+
+
 # ----------------------------------------------------------------------------- custom reward / declarative constraints
 def test_fused_ocp_reward_matches_reference_function(golden_dir):
     """custom_reward={'kind': 'ocp_tracking'} is evaluated in the kernel; the fixture's rewards were produced by
