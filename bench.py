@@ -162,6 +162,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--n-envs", type=int, default=N_ENVS, help="envs per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-chunks", type=int, default=8, help="time slices pipelined by make_env.rollout_host")
     ap.add_argument("--ref-envs-per-worker", type=int, default=48)
     ap.add_argument("--noise-mode", default="philox", choices=["philox", "philox_f32", "off"],
                     help="experiment knob; the headline is 'philox' (fp64 Box-Muller)")
@@ -248,14 +249,11 @@ def main():
     a_host = [r.cpu().pin_memory() for r in ring[:2]]
     out_host = None
     def one_e2e(i):
+        # public API with host buffers: actions H2D, kernel(s), obs/reward/done D2H, all inside; complete on return
         nonlocal out_host
         env.rewind()
-        out = env.rollout(a_host[i % 2], want_x=False)            # H2D copy of this step's actions inside
-        if out_host is None:
-            out_host = {k: torch.empty(out[k].shape, dtype=out[k].dtype).pin_memory() for k in ("obs", "reward", "done")}
-        for k in out_host:
-            out_host[k].copy_(out[k], non_blocking=True)          # D2H of the step's results
-        return out
+        out_host = env.rollout_host(a_host[i % 2], out=out_host, chunks=args.e2e_chunks)
+        return out_host
     Ke = max(3, min(K, 10))
     for i in range(2):
         one_e2e(i)

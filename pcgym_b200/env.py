@@ -493,6 +493,7 @@ class make_env:
             for k, v in self._theta_user.items():
                 self._theta[self._theta_names.index(k)] = torch.from_numpy(v).to(dev)
         self._bufs = {}
+        self._pipe = None
         self._a_step = z(1, self._a_lo.shape[0], n)
         self._o_lo = torch.from_numpy(self.observation_space_base.low.astype(np.float64)).to(dev)
         self._o_hi = torch.from_numpy(self.observation_space_base.high.astype(np.float64)).to(dev)
@@ -716,11 +717,66 @@ class make_env:
                 raise ValueError(f"z must be [K, {self.Nx_oracle}, {n}]")
         return self._launch(a, K, want_x=want_x, z=z)
 
-    def _launch(self, a, K, want_x, z=None):
+    def rollout_host(self, actions, out=None, chunks: int = 8, want_x: bool = False):
+        """`rollout` for HOST buffers: `actions` [K, nu_a, n_envs] float64 in (ideally pinned) host memory; returns
+        pinned host tensors obs [K, Nx, n], reward [K, n], done [K, n] (and x [K, nx, n] if `want_x`), reusing `out`
+        when given.  The K intervals are cut into `chunks` time slices -- contiguous in both the action and the
+        output layouts -- and pipelined over three streams: the host->device copy of slice c+1 and the
+        device->host copy of slice c-1 overlap the kernel of slice c (PCIe is full duplex), so the call costs about
+        max(H2D, D2H) instead of their sum.  The result is complete when the call returns (it synchronises)."""
+        if not self._dev_ready:
+            raise RuntimeError("call reset() before rollout_host()")
+        if self._host_reward:
+            raise NotImplementedError("rollout_host() needs a fused reward (see rollout())")
+        n, nu_a = self.n_envs, self._a_lo.shape[0]
+        a = actions if isinstance(actions, torch.Tensor) else torch.as_tensor(np.asarray(actions, dtype=np.float64))
+        if a.device.type != "cpu" or a.dtype != torch.float64 or a.ndim != 3 or a.shape[1:] != (nu_a, n):
+            raise ValueError(f"actions must be a float64 host tensor [K, {nu_a}, {n}]")
+        a = a.contiguous()
+        K = a.shape[0]
+        if self.t + K > self.N - 1:
+            raise IndexError(f"rollout of {K} steps from t = {self.t} exceeds the episode (N - 1 = {self.N - 1} steps)")
+        if self._desc.noise == nat.NOISE["external"]:
+            raise ValueError("noise_mode='external' is not supported by rollout_host()")
+        dev = self.device
+        keys = ("obs", "reward", "done") + (("x",) if want_x else ())
+        bufs = self._out_bufs(K, want_x)
+        if out is None:
+            out = {k: torch.empty(bufs[k].shape, dtype=bufs[k].dtype).pin_memory() for k in keys}
+        if self._pipe is None:
+            self._pipe = (torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev))
+        s_in, s_out = self._pipe
+        main = torch.cuda.current_stream(dev)
+        a_dev = self._bufs.get(("a_dev", K))
+        if a_dev is None:
+            a_dev = self._bufs[("a_dev", K)] = torch.empty(K, nu_a, n, dtype=torch.float64, device=dev)
+        s_in.wait_stream(main)                    # earlier work on the caller's stream may still read a_dev / bufs
+        s_out.wait_stream(main)
+        edges = np.linspace(0, K, max(1, min(int(chunks), K)) + 1).astype(int)
+        for k0, k1 in zip(edges[:-1], edges[1:]):
+            k0, k1 = int(k0), int(k1)
+            with torch.cuda.stream(s_in):
+                a_dev[k0:k1].copy_(a[k0:k1], non_blocking=True)
+                ev_in = torch.cuda.Event()
+                ev_in.record(s_in)
+            main.wait_event(ev_in)
+            self._launch(a_dev[k0:k1], k1 - k0, want_x, bufs={k: (v[k0:k1] if v is not None else None) for k, v in bufs.items()})
+            ev_k = torch.cuda.Event()
+            ev_k.record(main)
+            with torch.cuda.stream(s_out):
+                s_out.wait_event(ev_k)
+                for k in keys:
+                    out[k][k0:k1].copy_(bufs[k][k0:k1], non_blocking=True)
+        main.wait_stream(s_out)
+        torch.cuda.current_stream(dev).synchronize()
+        return out
+
+    def _launch(self, a, K, want_x, z=None, bufs=None):
         d = self._desc
         if d.noise == nat.NOISE["external"] and z is None:
             raise ValueError("noise_mode='external' needs the standard normals `z`")
-        bufs = self._out_bufs(K, want_x)
+        if bufs is None:
+            bufs = self._out_bufs(K, want_x)
         io = self._io(a, K, bufs, z)
         stream = torch.cuda.current_stream(self.device).cuda_stream
         with torch.cuda.device(self.device):

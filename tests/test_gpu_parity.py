@@ -85,6 +85,29 @@ def test_rollout_equals_repeated_steps_bitwise(name, golden_dir):
         assert same(e1.info["cons_info"], e2.info["cons_info"])
 
 
+@pytest.mark.parametrize("chunks", [1, 4, 7])
+def test_rollout_host_pipelined_equals_rollout_bitwise(chunks):
+    """make_env.rollout_host: time-sliced H2D / kernel / D2H pipeline over host buffers == one device rollout."""
+    params = cases.cstr_dist_cons()
+    n, K = 512, params["N"] - 1
+    rng = np.random.default_rng(4)
+    acts = torch.as_tensor(rng.uniform(-1, 1, (K, 1, n)))
+    e1 = _env(params, n_envs=n, integrator=HEADLINE, seed=5)
+    e2 = _env(params, n_envs=n, integrator=HEADLINE, seed=5)
+    e1.reset(); e2.reset()
+    ref = e1.rollout(acts.cuda())
+    out = e2.rollout_host(acts.pin_memory(), chunks=chunks, want_x=True)
+    for k in ("obs", "reward", "done", "x"):
+        assert out[k].device.type == "cpu" and out[k].is_pinned()
+        assert same(out[k].to(torch.float64), ref[k].cpu().to(torch.float64)), k
+    assert e2.t == K and torch.equal(e1.info["cons_info"], e2.info["cons_info"])
+    e2.reset()
+    out2 = e2.rollout_host(acts, out=out, chunks=chunks, want_x=True)
+    assert out2 is out and same(out["obs"], ref["obs"].cpu())
+    with pytest.raises(ValueError):
+        e2.rollout_host(acts.cuda())
+
+
 # ----------------------------------------------------------------------------- golden do-mpc trajectories through CUDA
 @pytest.mark.parametrize("model", ["cstr", "four_tank", "multistage_extraction", "crystallization", "biofilm_reactor"])
 def test_golden_trajectories_cuda(model, golden_dir):
