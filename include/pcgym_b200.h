@@ -38,7 +38,9 @@ extern "C" {
 #define PCG_MAX_ND     4   /* model disturbance channels                        */
 #define PCG_MAX_NTAIL  8   /* observation-only constants (uncertain parameters) */
 #define PCG_MAX_NCON   8   /* affine constraints                                */
-#define PCG_MAX_PARAM 16   /* model parameters theta                            */
+#define PCG_MAX_PARAM 32   /* model parameters theta (affine custom model 4x2: 28) */
+#define PCG_AFFINE_MAX_NX 4
+#define PCG_AFFINE_MAX_NU 2
 #define PCG_MAX_OBS   (PCG_MAX_NX + PCG_MAX_NSP + PCG_MAX_ND + PCG_MAX_NTAIL)
 
 /* model registry: reference src/pcgym/pcgym.py:128-148 (keys in comments) */
@@ -62,7 +64,12 @@ enum pcg_model {
   PCG_MODEL_OSCILLATORS = 16,     /* "coupled_oscillator"     model_classes.py:186 (N = 10; no inputs: 1 ignored row) */
   PCG_MODEL_DISEASE = 17,         /* "disease"                model_classes.py:156  */
   PCG_MODEL_HYDRAULIC_TANK = 18,  /* "hydraulic_tank"         model_classes.py:128  */
-  PCG_MODEL_COUNT = 19
+  /* env_params["custom_model"] (pcgym.py:150-153): a Python RHS cannot run in a kernel, but an AFFINE one
+   * dx = A x + B u + c -- the reference's own example, tests/environment/test_make_env_custom_model.py:7-26 -- is
+   * probed on the host and run by these; id = BASE + (nx - 1) * PCG_AFFINE_MAX_NU + (nu - 1);
+   * theta = A row-major (nx*nx), B row-major (nx*nu), c (nx); Tsit5 only. */
+  PCG_MODEL_AFFINE_BASE = 19,
+  PCG_MODEL_COUNT = 27
 };
 
 /* integrator: replaces integrator.py:90-107 (CVODES) / :65-88 (diffrax Tsit5 + PID 1e-8) */
@@ -95,7 +102,11 @@ enum pcg_flags {
   PCG_F_A_DELTA = 1 << 2,       /* pcgym.py:376-383 (only live with NORMALISE_A)    */
   PCG_F_R_PENALTY = 1 << 3,     /* pcgym.py:556-557 / :529-530                      */
   PCG_F_DONE_ON_VIOLATION = 1 << 4, /* pcgym.py:613-614                             */
-  PCG_F_ADAPTIVE = 1 << 5       /* embedded error control (DOPRI5 / TSIT5 only)     */
+  PCG_F_ADAPTIVE = 1 << 5,      /* embedded error control (DOPRI5 / TSIT5 only)     */
+  PCG_F_SP_HIDDEN = 1 << 6      /* x0 / o_space carry no setpoint slots: the observation is [x] only while the
+                                   reward still tracks SP (the reference's own custom-model test runs like this,
+                                   tests/environment/test_make_env_custom_model.py:66-86; numpy lets the
+                                   setpoint write at pcgym.py:437 fall off the end of the state vector)          */
 };
 
 enum pcg_status {

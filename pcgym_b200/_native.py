@@ -12,7 +12,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libpcgym_b200.so")
 
 ABI_VERSION = 2
-MAX_NX, MAX_NU, MAX_NSP, MAX_ND, MAX_NTAIL, MAX_NCON, MAX_PARAM = 24, 8, 4, 4, 8, 8, 16
+MAX_NX, MAX_NU, MAX_NSP, MAX_ND, MAX_NTAIL, MAX_NCON, MAX_PARAM = 24, 8, 4, 4, 8, 8, 32
+AFFINE_BASE, AFFINE_MAX_NX, AFFINE_MAX_NU = 19, 4, 2
 MAX_OBS = MAX_NX + MAX_NSP + MAX_ND + MAX_NTAIL
 
 MODEL_IDS = {
@@ -40,7 +41,7 @@ SCHEMES = {"rk4": 0, "dopri5": 1, "rk45": 1, "tsit5": 2}
 NOISE = {"off": 0, "philox": 1, "external": 2, "philox_f32": 3}
 REWARD = {"none": 0, "sp": 1, "batch": 2, "ocp": 3}
 
-F_NORMALISE_A, F_NORMALISE_O, F_A_DELTA, F_R_PENALTY, F_DONE_ON_VIOLATION, F_ADAPTIVE = (1 << i for i in range(6))
+F_NORMALISE_A, F_NORMALISE_O, F_A_DELTA, F_R_PENALTY, F_DONE_ON_VIOLATION, F_ADAPTIVE, F_SP_HIDDEN = (1 << i for i in range(7))
 ST_NONFINITE, ST_STEPCAP = 1, 2
 
 f64, i32, u32, i64, u64 = C.c_double, C.c_int32, C.c_uint32, C.c_int64, C.c_uint64

@@ -1,6 +1,7 @@
 // C ABI of libpcgym_b200.so: argument validation + dispatch to the per-model kernel launchers.
 // Declarations and the reference interface each entry point replaces: include/pcgym_b200.h.
 #include <atomic>
+#include <cstdio>
 #include <cstring>
 
 #include "launch.cuh"
@@ -57,6 +58,32 @@ const double kDiD[] = {0.3, 0.1};
 const char* const kHtN[] = {"D"};
 const double kHtD[] = {1.0};
 
+// affine custom models: theta = [A row-major | B row-major | c], defaults 0; parameter names a_i_j, b_i_j, c_i
+struct AffineNames {
+  char text[PCG_MAX_PARAM][8];
+  const char* ptr[PCG_MAX_PARAM];
+  AffineNames(int nx, int nu) {
+    int k = 0;
+    for (int i = 0; i < nx; ++i)
+      for (int j = 0; j < nx; ++j) std::snprintf(text[k++], 8, "a_%d_%d", i, j);
+    for (int i = 0; i < nx; ++i)
+      for (int j = 0; j < nu; ++j) std::snprintf(text[k++], 8, "b_%d_%d", i, j);
+    for (int i = 0; i < nx; ++i) std::snprintf(text[k++], 8, "c_%d", i);
+    for (int i = 0; i < PCG_MAX_PARAM; ++i) ptr[i] = i < k ? text[i] : "";
+  }
+};
+const double kZeros[PCG_MAX_PARAM] = {};
+template <int NX, int NU>
+cudaError_t launch_affine_t(const pcg_desc& d, const pcg_io& io, int64_t n, int t0, int k, cudaStream_t s) {
+  return pcg::launch_affine(NX, NU, d, io, n, t0, k, s);
+}
+template <int NX, int NU>
+ModelInfo affine_info() {
+  static const AffineNames names(NX, NU);
+  return ModelInfo{NX, NU, 0, NX * NX + NX * NU + NX, names.ptr, kZeros, launch_affine_t<NX, NU>};
+}
+#define PCG_AFFINE_ROW(NX, NU) affine_info<NX, NU>()
+
 template <class M>
 constexpr ModelInfo info(const char* const* n, const double* dflt, pcg::launch_fn f) {
   return ModelInfo{M::NX, M::NU, M::ND, M::NP, n, dflt, f};
@@ -82,6 +109,8 @@ const ModelInfo kModels[PCG_MODEL_COUNT] = {
     info<pcg::Oscillators>(kOsN, kOsD, pcg::launch_oscillators),
     info<pcg::Disease>(kDiN, kDiD, pcg::launch_disease),
     info<pcg::HydraulicTank>(kHtN, kHtD, pcg::launch_hydraulic_tank),
+    PCG_AFFINE_ROW(1, 1), PCG_AFFINE_ROW(1, 2), PCG_AFFINE_ROW(2, 1), PCG_AFFINE_ROW(2, 2),
+    PCG_AFFINE_ROW(3, 1), PCG_AFFINE_ROW(3, 2), PCG_AFFINE_ROW(4, 1), PCG_AFFINE_ROW(4, 2),
 };
 
 // the measurement-noise transform on caller-supplied Philox words (pcg_normal_pairs)
@@ -108,6 +137,7 @@ int validate(const pcg_desc* d, const pcg_io* io, int64_t n_env, int64_t t0, int
   if (d->scheme < 0 || d->scheme >= PCG_SCHEME_COUNT) return PCG_E_SCHEME;
   const bool adaptive = (d->flags & PCG_F_ADAPTIVE) != 0;
   if (adaptive && d->scheme == PCG_SCHEME_RK4) return PCG_E_SCHEME;
+  if (d->model >= PCG_MODEL_AFFINE_BASE && d->scheme != PCG_SCHEME_TSIT5) return PCG_E_SCHEME;   // Tsit5 kernels only
   const ModelInfo& m = kModels[d->model];
   if (d->nu_a != m.nu) return PCG_E_DIMS;
   if (d->model == PCG_MODEL_OSCILLATORS && d->theta[0] != pcg::Oscillators::NOSC) return PCG_E_DIMS;   // state count is 2 N

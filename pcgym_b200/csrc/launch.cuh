@@ -174,9 +174,18 @@ cudaError_t launch_g(const pcg_desc& d, const pcg_io& io, int64_t n_env, int t0,
                              : launch_e<M, TB, ADAPTIVE, false>(d, io, n_env, t0, k_steps, s);
 }
 
+template <class M, class = void>
+struct tsit5_only : std::false_type {};
+template <class M>
+struct tsit5_only<M, std::enable_if_t<M::TSIT5_ONLY>> : std::true_type {};
+
 template <class M>
 cudaError_t launch_model(const pcg_desc& d, const pcg_io& io, int64_t n_env, int t0, int k_steps, cudaStream_t s) {
   const bool adaptive = (d.flags & PCG_F_ADAPTIVE) != 0;
+  if constexpr (tsit5_only<M>::value) {          // abi.cu: validate() rejects the other schemes for these models
+    return adaptive ? launch_g<M, Tsit5, true>(d, io, n_env, t0, k_steps, s)
+                    : launch_g<M, Tsit5, false>(d, io, n_env, t0, k_steps, s);
+  }
   switch (d.scheme) {
     case PCG_SCHEME_RK4:
       return launch_g<M, Rk4, false>(d, io, n_env, t0, k_steps, s);
@@ -210,5 +219,6 @@ cudaError_t launch_batch(const pcg_desc&, const pcg_io&, int64_t, int, int, cuda
 cudaError_t launch_oscillators(const pcg_desc&, const pcg_io&, int64_t, int, int, cudaStream_t);
 cudaError_t launch_disease(const pcg_desc&, const pcg_io&, int64_t, int, int, cudaStream_t);
 cudaError_t launch_hydraulic_tank(const pcg_desc&, const pcg_io&, int64_t, int, int, cudaStream_t);
+cudaError_t launch_affine(int nx, int nu, const pcg_desc&, const pcg_io&, int64_t, int, int, cudaStream_t);
 
 }  // namespace pcg

@@ -355,6 +355,39 @@ struct HydraulicTank {
   }
 };
 
+// ---------------------------------------------------------------------------------------
+// Affine custom model  dx = A x + B u + c  (env_params["custom_model"], pcgym.py:150-153; the reference's example
+// tests/environment/test_make_env_custom_model.py:7-26 is of this form).  The host probes the user's callable for
+// affinity and passes theta = [A row-major | B row-major | c].  Tsit5 instantiations only.
+template <int NX_, int NU_>
+struct Affine {
+  static constexpr int NX = NX_, NU = NU_, ND = 0, NP = NX_ * NX_ + NX_ * NU_ + NX_;
+  struct P { double A[NX_][NX_], B[NX_][NU_], c[NX_]; };
+  PCG_HD static P make(const double* th) {
+    P p;
+    for (int i = 0; i < NX; ++i) {
+      for (int j = 0; j < NX; ++j) p.A[i][j] = th[i * NX + j];
+      for (int j = 0; j < NU; ++j) p.B[i][j] = th[NX * NX + i * NU + j];
+      p.c[i] = th[NX * NX + NX * NU + i];
+    }
+    return p;
+  }
+  PCG_HD static constexpr int dpar(int) { return -1; }
+  PCG_EXT_TRAITS
+  static constexpr bool TSIT5_ONLY = true;
+  PCG_DEV static void rhs(const P& p, const Aux&, const double* x, const double* u, double* dx) {
+#pragma unroll
+    for (int i = 0; i < NX; ++i) {
+      double acc = p.c[i];
+#pragma unroll
+      for (int j = 0; j < NX; ++j) acc = fma(p.A[i][j], x[j], acc);
+#pragma unroll
+      for (int j = 0; j < NU; ++j) acc = fma(p.B[i][j], u[j], acc);
+      dx[i] = acc;
+    }
+  }
+};
+
 #undef PCG_EXT_TRAITS
 
 }  // namespace pcg

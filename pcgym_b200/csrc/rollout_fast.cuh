@@ -39,7 +39,8 @@ fast_rollout_kernel(const __grid_constant__ pcg_desc d, const __grid_constant__ 
 
   const int flags = d.flags;
   const bool done_on_v = flags & PCG_F_DONE_ON_VIOLATION;
-  const int nsp = d.nsp, n_con = d.n_con, n_obs = NX + nsp;
+  const int nsp = d.nsp, n_con = d.n_con;
+  const int nsp_obs = (flags & PCG_F_SP_HIDDEN) ? 0 : nsp, n_obs = NX + nsp_obs;
   const double pen = d.penalty;
   const PhiloxKeys& key = dv.rk;
   const int t_last = d.N - 1;
@@ -159,7 +160,7 @@ fast_rollout_kernel(const __grid_constant__ pcg_desc d, const __grid_constant__ 
 #pragma unroll
       for (int e = 0; e < EPT; ++e)
         w[e] = fma(o.sp_cur[j][e], d.o_scale[NX + j], d.o_off[NX + j]);
-      if (j < nsp) st_row<EPT>(po + (NX + j) * n, w);
+      if (j < nsp_obs) st_row<EPT>(po + (NX + j) * n, w);
     }
     st_row<EPT>(pr, r);
     st_flags<EPT>(pd, done);

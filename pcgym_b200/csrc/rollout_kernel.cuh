@@ -261,7 +261,8 @@ rollout_kernel(const __grid_constant__ pcg_desc d, const __grid_constant__ pcg_i
   const bool dist_on = GENERAL && d.nd > 0;
   const int nsp = d.nsp, n_con = d.n_con;
   const int nd_obs = GENERAL ? d.nd_obs : 0, n_tail = GENERAL ? d.n_tail : 0;
-  const int n_obs = NX + nsp + nd_obs + n_tail;
+  const int nsp_obs = (flags & PCG_F_SP_HIDDEN) ? 0 : nsp;                     // setpoint slots of the observation
+  const int n_obs = NX + nsp_obs + nd_obs + n_tail;
   const int noise = d.noise;
 
   // ---- carried state
@@ -652,7 +653,7 @@ rollout_kernel(const __grid_constant__ pcg_desc d, const __grid_constant__ pcg_i
       }
 #pragma unroll
       for (int j = 0; j < NSPM; ++j)
-        if (j < nsp) {
+        if (j < nsp_obs) {
           const int i = NX + j;
           double v[EPT];
 #pragma unroll
@@ -663,7 +664,7 @@ rollout_kernel(const __grid_constant__ pcg_desc d, const __grid_constant__ pcg_i
 #pragma unroll
         for (int j = 0; j < NDOM; ++j)
           if (j < nd_obs) {
-            const int i = NX + nsp + j;
+            const int i = NX + nsp_obs + j;
             double v[EPT];
 #pragma unroll
             for (int e = 0; e < EPT; ++e) v[e] = norm_o ? fma(dslot[e][j], d.o_scale[i], d.o_off[i]) : dslot[e][j];
@@ -672,7 +673,7 @@ rollout_kernel(const __grid_constant__ pcg_desc d, const __grid_constant__ pcg_i
 #pragma unroll
         for (int j = 0; j < NTLM; ++j)
           if (j < n_tail) {
-            const int i = NX + nsp + nd_obs + j;
+            const int i = NX + nsp_obs + nd_obs + j;
             double v[EPT];
 #pragma unroll
             for (int e = 0; e < EPT; ++e) v[e] = norm_o ? fma(tail[e][j], d.o_scale[i], d.o_off[i]) : tail[e][j];

@@ -117,10 +117,15 @@ class make_env:
 
         # pcgym.py:127-158
         if P.get("custom_model") is not None:
-            raise NotImplementedError(
-                "custom_model is a Python callable and cannot run inside the CUDA kernel; "
-                "only registry models are supported by the B200 engine")
-        self.model = _models.get(P.get("model"), self.integration_method)
+            # env.model stays the user's object (pcgym.py:150-153); its affine RHS is read off it for the device
+            m = P["custom_model"]
+            self._dmodel = _models.AffineCustomModel(m)          # raises for a non-affine right-hand side
+            m.int_method = self.integration_method
+            self.model = m
+            if self.integrator["scheme"] != "tsit5":
+                raise ValueError("custom (affine) models run with the 'tsit5' integrator scheme")
+        else:
+            self.model = self._dmodel = _models.get(P.get("model"), self.integration_method)
         minfo = self.model.info()
 
         # pcgym.py:160-165
@@ -129,7 +134,7 @@ class make_env:
         # input-less models (invariant_batch, coupled_oscillator) take one ignored action entry (csrc/models_ext.cuh)
         self.Nu = max(len(minfo["inputs"]), 1)
         if n_a != self.Nu:
-            raise ValueError(f"a_space has {n_a} entries but model '{self.model.name}' has {self.Nu} inputs")
+            raise ValueError(f"a_space has {n_a} entries but model '{self._dmodel.name}' has {self.Nu} inputs")
 
         # pcgym.py:167-199
         self.disturbance_active = False
@@ -144,7 +149,7 @@ class make_env:
                     raise KeyError(str(k))                                         # pcgym.py:400 on the reference
             unknown = [k for k in self.disturbances if k not in (minfo.get("disturbances") or [])]
             if unknown:
-                raise KeyError(f"disturbances {unknown} are not channels of model '{self.model.name}' "
+                raise KeyError(f"disturbances {unknown} are not channels of model '{self._dmodel.name}' "
                                f"({minfo['disturbances']})")
             self.Nu += self.Nd_model
             self.Nx += self.Nd
@@ -176,16 +181,29 @@ class make_env:
         self._theta_user = {}
         for k, v in (P.get("model_params") or {}).items():
             if k not in self._theta_names:
-                raise AttributeError(f"{self.model.name} has no parameter {k!r}")
+                raise AttributeError(f"{self._dmodel.name} has no parameter {k!r}")
             v = _np(v).reshape(-1)
             if v.shape[0] not in (1, self.n_envs):
                 raise ValueError(f"model_params[{k!r}] must have n_envs = {self.n_envs} entries")
             self._theta_user[k] = np.broadcast_to(v, (self.n_envs,)).copy()
         self._per_env_theta = bool(self._theta_user) or self.uncertainty_in_dynamics
+        if self._per_env_theta and self._dmodel is not self.model:
+            raise NotImplementedError("per-env parameters are not supported for custom models")
         self.observation_space_base = Box(o_lo, o_hi)
         n_o = o_lo.shape[0]
         self.observation_space = Box(-np.ones(n_o), np.ones(n_o)) if self.normalise_o else self.observation_space_base
         self._n_obs = self.Nx + self.NUn
+        # The reference never checks len(x0): with x0 / o_space that carry NO setpoint slots the setpoint write
+        # (pcgym.py:437) falls off the end of the state vector and the observation is [x] only, while the reward
+        # still tracks SP -- its own custom-model test runs like this (test_make_env_custom_model.py:66-86).
+        n_sp = len(self.SP) if self.SP is not None else 0
+        x0_len = _np(self.x0).shape[-1]
+        self._sp_hidden = bool(n_sp and x0_len == self.Nx_oracle and n_o == self._n_obs - n_sp)
+        if self._sp_hidden:
+            if self.Nd or self.NUn:
+                raise NotImplementedError("x0 without setpoint slots together with observed disturbances / uncertain "
+                                          "parameters is not supported")
+            self._n_obs -= n_sp
         if n_o != self._n_obs:
             raise ValueError(f"o_space (+ disturbance/uncertainty bounds) has {n_o} entries, state vector has {self._n_obs}")
 
@@ -328,7 +346,7 @@ class make_env:
             x0 = np.broadcast_to(x0, (self.n_envs, x0.shape[0]))
         elif x0.shape[0] != self.n_envs:
             raise ValueError("per-env x0 must be [n_envs, Nx]")
-        need = self.Nx_oracle + len(self._sp_keys)
+        need = self.Nx_oracle + (0 if self._sp_hidden else len(self._sp_keys))
         if x0.shape[1] != need:
             raise ValueError(f"x0 has {x0.shape[1]} entries; expected {need} (model states + setpoints)")
         self._x0_host = np.ascontiguousarray(x0.T)        # [Nx_oracle + nsp, n_envs]
@@ -340,7 +358,7 @@ class make_env:
         nx = self.Nx_oracle
         names = self.model.info()["states"]
         d.abi_version, d.struct_bytes = nat.ABI_VERSION, ctypes.sizeof(nat.Desc)
-        d.model = self.model.model_id
+        d.model = self._dmodel.model_id
         d.scheme = nat.SCHEMES[self.integrator["scheme"]]
         flags = 0
         flags |= nat.F_NORMALISE_A if self.normalise_a is True else 0
@@ -350,18 +368,19 @@ class make_env:
         flags |= nat.F_R_PENALTY if self.r_penalty else 0
         flags |= nat.F_DONE_ON_VIOLATION if (self.constraint_active and self.done_on_constraint) else 0
         flags |= nat.F_ADAPTIVE if self.integrator["adaptive"] else 0
+        flags |= nat.F_SP_HIDDEN if self._sp_hidden else 0
         d.flags = flags
         d.n_sub, d.max_steps = int(self.integrator["n_sub"]), int(self.integrator["max_steps"])
         d.rtol, d.atol = float(self.integrator["rtol"]), float(self.integrator["atol"])
         d.N, d.dt = self.N, float(self.dt)
-        theta = self.model.theta()
+        theta = self._dmodel.theta()
         for i, v in enumerate(theta):
             d.theta[i] = v
 
         nu_a = self._a_lo.shape[0]
         d.nu_a = nu_a
         params = self.model.info()["parameters"]
-        model_d = [] if self.model.disturbances in (["None"], [], None) else self.model.disturbances
+        model_d = [] if self._dmodel.disturbances in (["None"], [], None) else self._dmodel.disturbances
         d.nd = len(model_d) if self.disturbance_active else 0
         for i in range(nat.MAX_ND):
             d.d_src[i] = -1
@@ -381,7 +400,7 @@ class make_env:
         for j, k in enumerate(self._sp_keys):
             d.sp_state[j] = names.index(k)
             d.r_scale[j] = float(r_scale.get(k, 1))
-            d.sp_init[j] = float(self._x0_host[nx + j, 0])
+            d.sp_init[j] = 0.0 if self._sp_hidden else float(self._x0_host[nx + j, 0])
         d.nd_obs = len(self._d_keys)
         for j, k in enumerate(self._d_keys):
             d.d_obs[j] = model_d.index(k)
@@ -809,7 +828,7 @@ class make_env:
         else:
             parts = [self._x]
             n = self.n_envs
-            if self._sp_dev is not None:
+            if self._sp_dev is not None and not self._sp_hidden:
                 parts.append(self._sp_dev[self.t - 1] if self._sp_per_env else self._sp_dev[:, self.t - 1: self.t].expand(-1, n))
             if self._d_dev is not None:
                 parts.append(self._d_dev[self.t] if self._d_per_env else self._d_dev[:, self.t: self.t + 1].expand(-1, n))

@@ -97,6 +97,47 @@ class DeviceModel:
             "(use oracle.rhs in tests if you need reference values)")
 
 
+class AffineCustomModel:
+    """Device side of `env_params["custom_model"]` (pcgym.py:150-153).  A Python RHS cannot run inside a kernel, but
+    an affine one dx = A x + B u + c can be read off the callable: c = f(0, 0), A[:, i] = f(e_i, 0) - c,
+    B[:, j] = f(0, e_j) - c, then checked at random points.  The reference's own example model
+    (tests/environment/test_make_env_custom_model.py:7-26) is of this form.  Anything else raises."""
+
+    def __init__(self, user_model, rng=None):
+        info = user_model.info()
+        self.name = "custom_model"
+        self.states, self.inputs = list(info["states"]), list(info["inputs"])
+        self.disturbances = info.get("disturbances")
+        if self.disturbances not in ([], None, ["None"]):
+            raise NotImplementedError("custom_model with disturbance channels is not supported by the B200 engine")
+        nx, nu = len(self.states), len(self.inputs)
+        if not (1 <= nx <= _native.AFFINE_MAX_NX and 1 <= nu <= _native.AFFINE_MAX_NU):
+            raise NotImplementedError(f"affine custom models are compiled for 1..{_native.AFFINE_MAX_NX} states and "
+                                      f"1..{_native.AFFINE_MAX_NU} inputs; got {nx} x {nu}")
+        import numpy as np
+        f = lambda x, u: np.asarray(user_model(np.asarray(x, float), np.asarray(u, float)), dtype=np.float64).reshape(-1)
+        c = f(np.zeros(nx), np.zeros(nu))
+        if c.shape != (nx,):
+            raise ValueError(f"custom_model returned {c.shape[0]} derivatives for {nx} states")
+        A = np.stack([f(np.eye(nx)[i], np.zeros(nu)) - c for i in range(nx)], axis=1)
+        B = np.stack([f(np.zeros(nx), np.eye(nu)[j]) - c for j in range(nu)], axis=1)
+        rng = rng or np.random.default_rng(0)
+        for _ in range(4):
+            x, u = rng.normal(size=nx) * 3.0, rng.normal(size=nu) * 3.0
+            want, got = f(x, u), A @ x + B @ u + c
+            if not np.allclose(got, want, rtol=1e-9, atol=1e-9 * (1 + np.abs(want).max())):
+                raise NotImplementedError(
+                    "custom_model is not affine in (x, u): a Python right-hand side cannot run inside the CUDA "
+                    "kernel; only affine custom models (dx = A x + B u + c) and the registry models are supported")
+        self.A, self.B, self.c = A, B, c
+        self.model_id = _native.AFFINE_BASE + (nx - 1) * _native.AFFINE_MAX_NU + (nu - 1)
+        dims = _native.model_dims(self.model_id)
+        assert dims[:2] == (nx, nu) and dims[3] == nx * nx + nx * nu + nx, "registry / library mismatch"
+
+    def theta(self):
+        return [float(v) for v in list(self.A.reshape(-1)) + list(self.B.reshape(-1)) + list(self.c)]
+
+
 def model_mapping():
     return {name: (lambda name=name, **kw: DeviceModel(name, **kw)) for name in _META}
 

@@ -94,6 +94,45 @@ def test_constraint_probe_rejects_non_affine():
         make_env(p)
 
 
+class _Custom:
+    """The reference's example custom model (tests/environment/test_make_env_custom_model.py:7-26)."""
+
+    def __init__(self, param1=1.5, param2=2.5, square=False):
+        self.int_method, self.param1, self.param2, self.square = "casadi", param1, param2, square
+
+    def __call__(self, x, u):
+        return np.array([self.param1 * (x[0] ** 2 if self.square else x[0]) + u[0], self.param2 * x[1]])
+
+    def info(self):
+        return {"parameters": {"param1": self.param1, "param2": self.param2}, "states": ["x1", "x2"],
+                "inputs": ["u1"], "disturbances": []}
+
+
+def _kat_params(**kw):
+    p = {"custom_model": _Custom(), "a_space": {"low": np.array([-1]), "high": np.array([1])},
+         "o_space": {"low": np.array([-1, -1]), "high": np.array([1, 1])}, "SP": {"x2": [2] * 100}, "N": 100,
+         "tsim": 10, "x0": np.array([1.0, 1.0])}
+    p.update(kw)
+    return p
+
+
+def test_custom_model_is_probed_for_affinity():
+    """env_params["custom_model"] (pcgym.py:150-153): env.model stays the user's object, int_method is set on it, the
+    affine map is read off the callable; x0 / o_space without setpoint slots give an observation of the states only."""
+    m = _Custom()
+    env = make_env(_kat_params(custom_model=m))
+    assert isinstance(env.model, _Custom) and env.model.int_method == "b200"     # a deep copy, as in the reference (pcgym.py:42)
+    np.testing.assert_array_equal(env._dmodel.A, [[1.5, 0.0], [0.0, 2.5]])
+    np.testing.assert_array_equal(env._dmodel.B, [[1.0], [0.0]])
+    np.testing.assert_array_equal(env._dmodel.c, [0.0, 0.0])
+    d = env._desc
+    assert d.model == nat.AFFINE_BASE + 2 and list(d.theta)[:8] == [1.5, 0.0, 0.0, 2.5, 1.0, 0.0, 0.0, 0.0]
+    assert (env.Nx_oracle, env.Nx, env._n_obs) == (2, 3, 2) and d.flags & nat.F_SP_HIDDEN and d.nsp == 1
+    assert env.observation_space.shape == (2,)
+    with pytest.raises(ValueError):
+        make_env(_kat_params(integrator={"scheme": "dopri5"}))
+
+
 def test_errors_like_reference():
     with pytest.raises(ValueError):
         make_env([1, 2])
@@ -101,8 +140,8 @@ def test_errors_like_reference():
         make_env(dict(cases.first_order(), model="nope"))
     with pytest.raises(ValueError):                      # a_space length must match the model's inputs
         make_env(dict(cases.first_order(), model="heat_exchanger"))
-    with pytest.raises(NotImplementedError):             # custom Python RHS cannot run in the kernel
-        make_env(dict(cases.first_order(), custom_model=object()))
+    with pytest.raises(NotImplementedError):             # a non-affine Python RHS cannot run in the kernel
+        make_env(dict(_kat_params(), custom_model=_Custom(square=True)))
     with pytest.raises(KeyError):                        # four_tank's only disturbance key is "None" (pcgym.py:400)
         make_env(dict(cases.four_tank(), disturbances={"q1": np.ones(24)},
                       disturbance_bounds={"low": np.array([0.0]), "high": np.array([2.0])}))

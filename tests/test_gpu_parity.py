@@ -438,6 +438,48 @@ def test_uncertainty_is_observation_only():
     assert rel(env._x.cpu().numpy(), x) < 1e-9
 
 
+def test_reference_known_answer_custom_model_through_cuda(golden_dir):
+    """The reference's only numeric assertion on the integration path
+    (tests/environment/test_make_env_custom_model.py:66-86: custom linear model, x0 = [1, 1], u = 0.5, dt = 0.1,
+    obs ~= [1.21578082, 1.28403262] under np.isclose) run through the CUDA path: the custom model's affine RHS is
+    read off the Python callable and integrated by the Affine<2,1> kernel."""
+    from test_env_host import _Custom, _kat_params
+    g = np.load(os.path.join(golden_dir, "kat_custom_model.npz"))
+    env = _env(_kat_params(custom_model=_Custom(param1=1.5, param2=2.5)))
+    obs0, _ = env.reset()
+    assert isinstance(env.model, _Custom) and obs0.shape == (2,) and np.allclose(obs0, [1.0, 1.0])
+    np.testing.assert_allclose(obs0, g["obs0"], rtol=0, atol=1e-15)
+    obs, r, done, trunc, info = env.step(np.array([0.5]))
+    assert obs.shape == (2,) and isinstance(r, float) and done is False and trunc is False
+    assert np.all(np.isclose(obs, g["asserted"]))                            # the reference test's own check (rtol 1e-5)
+    exact = np.array([(1 + 1 / 3) * np.exp(0.15) - 1 / 3, np.exp(0.25)])     # closed form of the linear ODE
+    np.testing.assert_allclose(obs, exact, rtol=1e-9)
+    np.testing.assert_allclose(obs, g["obs"], rtol=1e-9)                     # reference make_env + converged scipy
+    np.testing.assert_allclose(r, float(g["reward"]), rtol=1e-8)
+    # batched, 2 inputs, offset vector
+    class Two:
+        int_method = "casadi"
+        def __call__(self, x, u):
+            return np.array([-x[0] + 0.5 * x[2] + u[0] + 0.1, -2 * x[1] + u[1], x[0] - x[2] - 0.3])
+        def info(self):
+            return {"parameters": {}, "states": ["a", "b", "c"], "inputs": ["p", "q"], "disturbances": []}
+    n, K = 64, 6
+    rng = np.random.default_rng(2)
+    x0 = rng.uniform(-1, 1, (n, 3))
+    p = {"custom_model": Two(), "n_envs": n, "N": K + 1, "tsim": (K + 1) * 0.2, "SP": {"b": [0.0] * (K + 1)},
+         "x0": np.concatenate([x0, np.zeros((n, 1))], axis=1), "normalise_a": False, "normalise_o": False,
+         "a_space": {"low": -np.ones(2), "high": np.ones(2)}, "o_space": {"low": -np.ones(4), "high": np.ones(4)},
+         "integrator": {"scheme": "tsit5", "adaptive": True, "rtol": 1e-11, "atol": 1e-13}}
+    env = _env(p)
+    env.reset()
+    acts = rng.uniform(-1, 1, (K, 2, n))
+    out = env.rollout(torch.as_tensor(acts))
+    x = x0.T.copy()
+    for k in range(K):
+        x = oint.advance_dense(Two(), x, acts[k], 0.2, n_sub=64)
+        np.testing.assert_allclose(out["x"][k].cpu().numpy(), x, rtol=1e-8, atol=1e-10, err_msg=str(k))
+
+
 def test_per_env_parameters_reach_the_dynamics():
     """Row f4 (extension): `model_params` rows and, with uncertainty_in_dynamics, the sampled uncertain parameters
     drive each env's own RHS; the oracle integrates the same RHS with per-env parameter arrays."""
