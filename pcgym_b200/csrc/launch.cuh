@@ -5,7 +5,7 @@
 
 #include <cstdlib>
 
-#include "rollout_ws.cuh"
+#include "rollout_wsm.cuh"
 
 namespace pcg {
 
@@ -22,7 +22,8 @@ inline bool vector_ok(const pcg_io& io, int64_t n) {
   const void* f64[] = {io.x, io.a, io.a_save, io.z, io.tail, io.x_traj, io.obs, io.reward, io.g, io.g0, io.u_prev, io.theta};
   for (const void* p : f64)
     if (!al16(p)) return false;
-  return (reinterpret_cast<uintptr_t>(io.done) & 1u) == 0 && (reinterpret_cast<uintptr_t>(io.violated) & 1u) == 0;
+  return (reinterpret_cast<uintptr_t>(io.done) & 1u) == 0 && (reinterpret_cast<uintptr_t>(io.violated) & 1u) == 0 &&
+         (reinterpret_cast<uintptr_t>(io.done_state) & 1u) == 0;
 }
 
 template <class M>
@@ -144,6 +145,62 @@ cudaError_t launch_ws(const pcg_desc& d0, const pcg_io& io, int64_t n_env, int t
   return cudaGetLastError();
 }
 
+// persistent CTA per SM with a dynamically balanced finisher pool (rollout_wsm.cuh)
+inline int sm_count() {
+  static const int sms = [] {
+    int dev = 0, v = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    return v > 0 ? v : 148;
+  }();
+  return sms;
+}
+
+// eligible when every SM gets 2..8 tiles of 64 envs and `done` cannot depend on earlier violations
+inline bool wsm_ok(const pcg_desc& d, const pcg_io& io, int64_t n_env, int64_t k_steps, int64_t* envs_per_cta,
+                   int* n_tiles) {
+  if (d.flags & PCG_F_DONE_ON_VIOLATION) return false;
+  // the finishers address with 32-bit element indices
+  const int64_t lim = int64_t{1} << 31;
+  if (k_steps * PCG_MAX_OBS * n_env >= lim) return false;
+  if (io.sp_st < 0 || io.sp_sj < 0 || io.sp_se < 0 ||
+      (d.N + 1) * io.sp_st + PCG_MAX_NSP * io.sp_sj + (n_env + 2) * io.sp_se >= lim) return false;
+  const int64_t sms = sm_count();
+  const int64_t epc = 2 * ((n_env + 2 * sms - 1) / (2 * sms));
+  const int tiles = static_cast<int>((epc + 63) / 64);
+  *envs_per_cta = epc;
+  *n_tiles = tiles;
+  return tiles >= 2 && tiles < kWsmMaxTiles;       // 8 tiles per SM: the 255-register kernel is ahead (profiles/)
+}
+
+template <class M, class TB, int NOISE>
+cudaError_t launch_wsm_n(const pcg_desc& d, const pcg_io& io, const Derived<M, TB>& dv, int64_t n_env, int t0,
+                         int k_steps, cudaStream_t s, int64_t epc, int n_tiles) {
+  // > 48 KB of dynamic shared memory needs the opt-in, once per kernel instantiation
+  static const cudaError_t attr = cudaFuncSetAttribute(wsm_rollout_kernel<M, TB, NOISE>,
+                                                       cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                       static_cast<int>(sizeof(WsmShared<M>)));
+  if (attr != cudaSuccess) return attr;
+  const unsigned grid = static_cast<unsigned>((n_env + epc - 1) / epc);
+  wsm_rollout_kernel<M, TB, NOISE><<<grid, 32 * kWsmWarps, sizeof(WsmShared<M>), s>>>(d, io, dv, n_env, t0, k_steps,
+                                                                                        epc, n_tiles);
+  return cudaGetLastError();
+}
+
+template <class M, class TB>
+cudaError_t launch_wsm(const pcg_desc& d0, const pcg_io& io, int64_t n_env, int t0, int k_steps, cudaStream_t s,
+                       int64_t epc, int n_tiles) {
+  const pcg_desc d = fold_desc<M>(d0);
+  const Derived<M, TB> dv = make_derived<M, TB>(d);
+  cudaError_t e;
+  switch (d.noise) {
+    case PCG_NOISE_OFF: e = launch_wsm_n<M, TB, PCG_NOISE_OFF>(d, io, dv, n_env, t0, k_steps, s, epc, n_tiles); break;
+    case PCG_NOISE_PHILOX: e = launch_wsm_n<M, TB, PCG_NOISE_PHILOX>(d, io, dv, n_env, t0, k_steps, s, epc, n_tiles); break;
+    default: e = launch_wsm_n<M, TB, PCG_NOISE_PHILOX_F32>(d, io, dv, n_env, t0, k_steps, s, epc, n_tiles); break;
+  }
+  t_last_kernel = "wsm_rollout_kernel (persistent CTA per SM: integrator warps + finisher pool)";
+  return e;
+}
+
 template <class M, class TB, bool ADAPTIVE, bool GENERAL>
 cudaError_t launch_e(const pcg_desc& d, const pcg_io& io, int64_t n_env, int t0, int k_steps, cudaStream_t s) {
   // two envs per thread share one Philox block, which needs an even global id for the first of them
@@ -152,6 +209,12 @@ cudaError_t launch_e(const pcg_desc& d, const pcg_io& io, int64_t n_env, int t0,
     if (fast_ok<M>(d, io)) {
       if constexpr (M::EPT == 2) {
         if constexpr (M::WS > 0) {
+          // PCG_WS=3 forces / PCG_WSM=0 forbids the per-SM kernel (profiling knobs)
+          static const bool wsm_off = [] { const char* e = std::getenv("PCG_WSM"); return e && std::atoi(e) == 0; }();
+          int64_t epc = 0;
+          int tiles = 0;
+          if (two && wsm_ok(d, io, n_env, k_steps, &epc, &tiles) && (ws_override() == 3 || (ws_override() < 0 && !wsm_off)))
+            return launch_wsm<typename M::WsModel, TB>(d, io, n_env, t0, k_steps, s, epc, tiles);
           const int w = ws_override() < 0 ? (ws_preferred(n_env) ? M::WS : 0) : ws_override();
           // the integrator warps run the model's WsModel (cstr: Horner-form exp, 3 FP64 issue slots fewer per RHS)
           if (two && w == 1) return launch_ws<typename M::WsModel, TB, 1>(d, io, n_env, t0, k_steps, s);

@@ -22,7 +22,7 @@
 
 namespace pcg {
 
-constexpr int kWsRing = 4;         // power of two
+constexpr int kWsRing = 8;         // power of two
 
 PCG_DEV uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 PCG_DEV void mbar_init(uint64_t* b, int count) {

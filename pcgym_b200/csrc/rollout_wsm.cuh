@@ -1,0 +1,343 @@
+// One persistent CTA per SM, warp-specialised, with DYNAMICALLY balanced finisher work.
+//
+// Why it exists (profiles/README.md): rollout_ws.cuh ties each finisher warp to one integrator warp.  At the headline
+// batch (65 536 envs = 6.92 tiles of 64 envs per SM) seven such pairs land on four warp schedulers as 4+4+3+3 warps,
+// the two schedulers that carry two integrator warps AND two finisher warps set the pace, and the kernel loses
+// ~25 % to that quantisation.  Here a CTA of 16 warps owns everything its SM has to do (up to 8 tiles):
+//   * warps 0..NI-1 integrate one tile each (serial in time; identical to the integrator role of rollout_ws.cuh);
+//   * the other 16-NI warps are a POOL of finishers.  The finishing work of tile p at interval k -- Gaussian draws,
+//     constraints, reward, observation, all global traffic, and the prefetch of the action rows of interval k+R --
+//     is a task q = k*NI + p that any finisher takes from a shared counter.  Finishers on a scheduler that carries
+//     only one integrator warp get more issue slots, finish their tasks sooner and therefore take more of them:
+//     the load evens out across the four schedulers without any static partition.
+// A task is stateless given (p, k) as long as `done` does not depend on earlier violations, so the kernel requires
+// done_on_cons_vio == False (the launcher falls back otherwise).  Same ring / mbarrier hand-over as rollout_ws.cuh.
+#pragma once
+#include "rollout_ws.cuh"
+
+namespace pcg {
+
+constexpr int kWsmWarps = 16;      // 512 threads, 128 registers: one CTA fills an SM
+constexpr int kWsmMaxTiles = 8;    // integrator warps per CTA (<= 512 envs per SM)
+
+template <class M>
+struct WsmShared {
+  WsPair<M> tile[kWsmMaxTiles];
+  uchar2 done0[kWsmMaxTiles][32];   // sticky done flag each env entered the launch with
+  int slot_seq[kWsmMaxTiles][kWsRing];   // finished tasks per ring slot (see the task loop)
+  int next_task;
+};
+
+template <class M, class TB, int NOISE>
+__global__ void __launch_bounds__(32 * kWsmWarps, 1)
+wsm_rollout_kernel(const __grid_constant__ pcg_desc d, const __grid_constant__ pcg_io io,
+                   const __grid_constant__ Derived<M, TB> dv, const int64_t n, const int t0, const int k_steps,
+                   const int64_t envs_per_cta, const int n_tiles) {
+  constexpr int NX = M::NX, NU = M::NU, ND = M::ND, NUK = NU + ND, EPT = 2, R = kWsRing;
+  extern __shared__ __align__(16) unsigned char wsm_raw[];
+  WsmShared<M>& sh = *reinterpret_cast<WsmShared<M>*>(wsm_raw);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t cta_base = static_cast<int64_t>(blockIdx.x) * envs_per_cta;
+  const int64_t cta_end = (cta_base + envs_per_cta < n) ? cta_base + envs_per_cta : n;
+
+  // lanes that own envs in tile p (the last tile of a CTA may be partial; envs_per_cta and n are even)
+  auto tile_lanes = [&](int p) {
+    const int64_t left = (cta_end - (cta_base + static_cast<int64_t>(p) * 64)) / 2;
+    return left < 0 ? 0 : (left > 32 ? 32 : static_cast<int>(left));
+  };
+  if (warp < n_tiles && lane == 0) {
+    const int cnt = tile_lanes(warp) > 0 ? tile_lanes(warp) : 1;
+#pragma unroll
+    for (int s = 0; s < R; ++s) {
+      mbar_init(&sh.tile[warp].full_a[s], cnt);
+      mbar_init(&sh.tile[warp].full_x[s], cnt);
+    }
+  }
+  if (threadIdx.x == 0) sh.next_task = 0;
+  if (threadIdx.x < kWsmMaxTiles * kWsRing) (&sh.slot_seq[0][0])[threadIdx.x] = 0;
+  __syncthreads();
+
+  auto to_uk = [&](const double (&a_raw)[NU][EPT], double (&uk)[EPT][NUK]) {   // pcgym.py:372-375, 386-414
+#pragma unroll
+    for (int e = 0; e < EPT; ++e) {
+#pragma unroll
+      for (int j = 0; j < NU; ++j) uk[e][j] = fma(a_raw[j][e], d.a_scale[j], d.a_off[j]);
+#pragma unroll
+      for (int i = 0; i < ND; ++i) uk[e][NU + i] = d.d_default[i];
+    }
+  };
+
+  if (warp < n_tiles) {
+    // ================================================================ integrator warp of tile `warp`
+    if (lane >= tile_lanes(warp)) return;
+    WsPair<M>& sp = sh.tile[warp];
+    const int64_t env0 = cta_base + static_cast<int64_t>(warp) * 64 + 2 * lane;
+    double x[EPT][NX];
+#pragma unroll
+    for (int i = 0; i < NX; ++i) {
+      double v[EPT];
+      ld_row<EPT>(io.x + i * n + env0, v);
+#pragma unroll
+      for (int e = 0; e < EPT; ++e) x[e][i] = v[e];
+    }
+    // the finishers read the initial state for the t == 0 pre-check before they release interval 0, so io.x may be
+    // overwritten at the end without a race
+#pragma unroll 1
+    for (int k = 0; k < k_steps; ++k) {
+      const int s = k & (R - 1);
+      mbar_wait(&sp.full_a[s], (k / R) & 1);
+      double a_raw[NU][EPT];
+#pragma unroll
+      for (int j = 0; j < NU; ++j) {
+        const double2 t = sp.a[s][j][lane];
+        a_raw[j][0] = t.x;
+        a_raw[j][1] = t.y;
+      }
+      double uk[EPT][NUK];
+      to_uk(a_raw, uk);
+      typename M::Aux aux[EPT];
+#pragma unroll
+      for (int e = 0; e < EPT; ++e) M::prep(dv.p, uk[e], aux[e]);
+      rk_step_fixed<M, TB, EPT>(dv, aux, x, uk);                               // integrator.py:90-107
+#pragma unroll
+      for (int i = 0; i < NX; ++i) sp.x[s][i][lane] = make_double2(x[0][i], x[1][i]);
+      mbar_arrive(&sp.full_x[s]);
+    }
+    unsigned status[EPT] = {0, 0};
+#pragma unroll
+    for (int i = 0; i < NX; ++i) {
+      double v[EPT];
+#pragma unroll
+      for (int e = 0; e < EPT; ++e) {
+        v[e] = x[e][i];
+        if (!isfinite(v[e])) status[e] |= PCG_ST_NONFINITE;
+      }
+      st_row<EPT>(io.x + i * n + env0, v);
+    }
+#pragma unroll
+    for (int e = 0; e < EPT; ++e) {
+      if (io.status && status[e]) io.status[env0 + e] |= static_cast<uint8_t>(status[e]);
+      if (io.n_rhs) io.n_rhs[env0 + e] += k_steps * TB::S;
+    }
+    return;
+  }
+
+  // ================================================================== finisher pool
+  const int fin = warp - n_tiles, n_fin = kWsmWarps - n_tiles;
+  const int flags = d.flags;
+  const int nsp = d.nsp, n_con = d.n_con;
+  const int nsp_obs = (flags & PCG_F_SP_HIDDEN) ? 0 : nsp, n_obs = NX + nsp_obs;
+  const double pen = d.penalty;
+  const PhiloxKeys& key = dv.rk;
+  const int t_last = d.N - 1;
+
+  // g = G [x; uk] + h, dense; rows >= n_con are zero-filled by the host so they can never flag
+  // (addresses in the finisher are 32-bit element indices off the array bases -- one IMAD.WIDE each; wsm_ok()
+  // checks that every array of the launch has fewer than 2^31 elements)
+  const uint32_t n32 = static_cast<uint32_t>(n);
+  auto constraints = [&](const double (&xs)[EPT][NX], const double (&uk)[EPT][NUK], double* gout, uint32_t gidx,
+                         bool (&viol)[EPT]) {
+#pragma unroll
+    for (int e = 0; e < EPT; ++e) viol[e] = false;
+#pragma unroll
+    for (int c = 0; c < kFastNcon; ++c) {
+      double g[EPT];
+#pragma unroll
+      for (int e = 0; e < EPT; ++e) {
+        double acc = d.con_h[c];
+#pragma unroll
+        for (int i = 0; i < NX; ++i) acc = fma(d.con_gx[c][i], xs[e][i], acc);
+#pragma unroll
+        for (int i = 0; i < NUK; ++i) acc = fma(d.con_gu[c][i], uk[e][i], acc);
+        g[e] = acc;
+        viol[e] = viol[e] || (acc > 0.0);
+      }
+      if (gout != nullptr && c < n_con) st_row<EPT>(gout + (gidx + c * n32), g);
+    }
+  };
+
+  // ---- prologue, tiles dealt round-robin to the finishers: t == 0 pre-check on the initial state, then the
+  // first R intervals' action rows into the ring (which releases the tile's integrator)
+#pragma unroll 1
+  for (int p = fin; p < n_tiles; p += n_fin) {
+    if (lane >= tile_lanes(p)) continue;
+    WsPair<M>& sp = sh.tile[p];
+    const int64_t env0 = cta_base + static_cast<int64_t>(p) * 64 + 2 * lane;
+    const double* pa = io.a + env0;
+    double a0[NU][EPT];
+#pragma unroll
+    for (int j = 0; j < NU; ++j) ld_row<EPT>(pa + j * n, a0[j]);
+    sh.done0[p][lane] = io.done_state ? *reinterpret_cast<const uchar2*>(io.done_state + env0) : make_uchar2(0, 0);
+    if (t0 == 0 && n_con > 0) {                                                // pcgym.py:416-420
+      double x0[EPT][NX], uk0[EPT][NUK];
+#pragma unroll
+      for (int i = 0; i < NX; ++i) {
+        double v[EPT];
+        ld_row<EPT>(io.x + i * n + env0, v);
+        x0[0][i] = v[0];
+        x0[1][i] = v[1];
+      }
+      to_uk(a0, uk0);
+      bool v0[EPT];
+      constraints(x0, uk0, io.g0, static_cast<uint32_t>(env0), v0);
+    }
+#pragma unroll
+    for (int s = 0; s < R; ++s) {
+      if (s < k_steps) {
+#pragma unroll
+        for (int j = 0; j < NU; ++j) {
+          double v[EPT];
+          ld_row<EPT>(pa + (static_cast<int64_t>(s) * NU + j) * n, v);
+          sp.a[s][j][lane] = make_double2(v[0], v[1]);
+        }
+        mbar_arrive(&sp.full_a[s]);
+      }
+    }
+  }
+
+  // ---- task loop
+  const int n_tasks = k_steps * n_tiles;
+#pragma unroll 1
+  while (true) {
+    int q = 0;
+    if (lane == 0) q = atomicAdd(&sh.next_task, 1);
+    q = __shfl_sync(0xffffffffu, q, 0);
+    if (q >= n_tasks) break;
+    const int k = q / n_tiles, p = q - k * n_tiles;
+    if (lane >= tile_lanes(p)) continue;
+    WsPair<M>& sp = sh.tile[p];
+    const int s = k & (R - 1);
+    const int t = t0 + k, t_new = t + 1;                                       // pcgym.py:441
+    const uint32_t env0 = static_cast<uint32_t>(cta_base) + static_cast<uint32_t>(p) * 64u + 2u * lane;
+    const uint32_t kn = static_cast<uint32_t>(k) * n32;
+
+    // action rows of interval k + R for this tile (row clamped at the last interval instead of branching)
+    const bool more = k + R < k_steps;
+    const uint32_t k_pre = more ? k + R : k_steps - 1;
+    double a_pre[NU][EPT];
+#pragma unroll
+    for (int j = 0; j < NU; ++j) ld_row<EPT>(io.a + ((k_pre * NU + j) * n32 + env0), a_pre[j]);
+
+    // SP[t] (shown in the observation) and SP[t+1] (enters the reward)
+    double spc[kFastNsp][EPT], spn[kFastNsp][EPT];
+    const uint32_t sp_st = static_cast<uint32_t>(io.sp_st), sp_se = static_cast<uint32_t>(io.sp_se);
+#pragma unroll
+    for (int j = 0; j < kFastNsp; ++j) {
+      const uint32_t jj = j < nsp ? j : 0;
+      const uint32_t si = jj * static_cast<uint32_t>(io.sp_sj) + env0 * sp_se + static_cast<uint32_t>(t) * sp_st;
+#pragma unroll
+      for (int e = 0; e < EPT; ++e) {
+        spc[j][e] = io.sp[si + e * sp_se];
+        spn[j][e] = io.sp[si + e * sp_se + sp_st];
+      }
+    }
+
+    // Gaussian draws of this interval: a pure function of (seed, env, t), computed while the integrator works
+    double z[EPT][NX];
+#pragma unroll
+    for (int e = 0; e < EPT; ++e)
+#pragma unroll
+      for (int i = 0; i < NX; ++i) z[e][i] = 0.0;
+    if constexpr (NOISE != PCG_NOISE_OFF) {
+      const uint64_t gid0 = static_cast<uint64_t>(d.env_id0) + env0;            // even: launch.cuh checks env_id0
+#pragma unroll
+      for (int i = 0; i < NX; i += 2) {
+        double za[EPT], zb[EPT];
+        draw_state_pair<EPT, NOISE == PCG_NOISE_PHILOX_F32>(gid0, static_cast<uint32_t>(t_new), i / 2, key, za, zb);
+#pragma unroll
+        for (int e = 0; e < EPT; ++e) {
+          z[e][i] = za[e];
+          if (i + 1 < NX) z[e][i + 1] = zb[e];
+        }
+      }
+    }
+    // An mbarrier wait names its phase by PARITY only, so it may look one phase ahead at most; with more finishers
+    // than ring slots per tile a finisher can hold interval k while k - R is still being finished by another one.
+    // slot_seq counts the finished tasks of a slot: wait for the predecessor first, then for the integrator.
+    const int c = k / R;
+    if (c > 0) {
+      const volatile int* seq = &sh.slot_seq[p][s];
+      while (*seq < c) __nanosleep(64);
+      __threadfence_block();
+    }
+    mbar_wait(&sp.full_x[s], c & 1);
+    // (written in the prologue before the tile's ring was released: ordered by the full_a -> full_x chain)
+    const uchar2 d0 = sh.done0[p][lane];
+    const bool done0[EPT] = {d0.x != 0, d0.y != 0};
+    double xe[EPT][NX], a_raw[NU][EPT], uk[EPT][NUK];
+#pragma unroll
+    for (int i = 0; i < NX; ++i) {
+      const double2 v = sp.x[s][i][lane];
+      xe[0][i] = v.x;
+      xe[1][i] = v.y;
+    }
+#pragma unroll
+    for (int j = 0; j < NU; ++j) {
+      const double2 v = sp.a[s][j][lane];
+      a_raw[j][0] = v.x;
+      a_raw[j][1] = v.y;
+    }
+    to_uk(a_raw, uk);
+
+    const uint32_t row = kn + env0;                                            // element [k][env0] of the [K][n] arrays
+    bool violated[EPT], done[EPT];
+    constraints(xe, uk, io.g, kn * n_con + env0, violated);                    // pcgym.py:444-446
+    const bool last = t_new == t_last;                                         // pcgym.py:448-449
+    double r[EPT];
+#pragma unroll
+    for (int e = 0; e < EPT; ++e) {
+      done[e] = done0[e] || last;                                              // done_on_cons_vio is off (launcher)
+      double acc = 0.0;
+#pragma unroll
+      for (int j = 0; j < kFastNsp; ++j) {                                     // r_scale[j >= nsp] == 0
+        const double err = pick<NX>(xe[e], d.sp_state[j]) - spn[j][e];
+        acc = fma(-(err * err), d.r_scale[j], acc);                            // pcgym.py:555
+        acc -= (violated[e] && j < nsp) ? pen : 0.0;                           // once per SP key (pcgym.py:556)
+      }
+      r[e] = acc;
+    }
+    const uint32_t ix = kn * NX + env0, io_ = kn * n_obs + env0;
+#pragma unroll
+    for (int i = 0; i < NX; ++i) {
+      double v[EPT], w[EPT];
+#pragma unroll
+      for (int e = 0; e < EPT; ++e) {
+        v[e] = xe[e][i];
+        const double ox = (NOISE != PCG_NOISE_OFF) ? fma(z[e][i] * xe[e][i], d.noise_pct[i], xe[e][i]) : xe[e][i];
+        w[e] = fma(ox, d.o_scale[i], d.o_off[i]);          // pcgym.py:483-493, 495-498 (folded: fold_desc)
+      }
+      st_row<EPT>(io.x_traj + (ix + i * n32), v);
+      st_row<EPT>(io.obs + (io_ + i * n32), w);
+    }
+#pragma unroll
+    for (int j = 0; j < kFastNsp; ++j) {
+      double w[EPT];
+#pragma unroll
+      for (int e = 0; e < EPT; ++e) w[e] = fma(spc[j][e], d.o_scale[NX + j], d.o_off[NX + j]);
+      if (j < nsp_obs) st_row<EPT>(io.obs + (io_ + (NX + j) * n32), w);
+    }
+    st_row<EPT>(io.reward + row, r);
+    st_flags<EPT>(io.done + row, done);
+    st_flags<EPT>(io.violated + row, violated);
+
+    if (more) {                                                                // hand interval k + R to the integrator
+#pragma unroll
+      for (int j = 0; j < NU; ++j) sp.a[s][j][lane] = make_double2(a_pre[j][0], a_pre[j][1]);
+      mbar_arrive(&sp.full_a[s]);
+    }
+    {                                                                          // this slot's task c is finished
+      const int tl = tile_lanes(p);
+      __syncwarp(tl == 32 ? 0xffffffffu : ((1u << tl) - 1u));
+      if (lane == 0) {
+        __threadfence_block();
+        *const_cast<volatile int*>(&sh.slot_seq[p][s]) = c + 1;
+      }
+    }
+    if (k == k_steps - 1 && io.done_state) {                                   // the sticky flag after this launch
+#pragma unroll
+      for (int e = 0; e < EPT; ++e) io.done_state[env0 + e] = done[e] ? 1 : 0;
+    }
+  }
+}
+
+}  // namespace pcg
