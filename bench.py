@@ -40,7 +40,7 @@ K_STEPS = N_HORIZON - 1
 # SURVEY 8(d) quotes 82 B because it assumes per-env setpoint tensors (8 B more read per env-step); the
 # headline uses the reference's shared setpoint schedule, which costs no per-env traffic.
 BYTES_PER_ENV_STEP = 74
-NCU_DRAM_BYTES_PER_LAUNCH = 53325056 + 371124224      # profiles/r1_cstr_v6_mono_ncu_summary.txt
+NCU_DRAM_BYTES_PER_LAUNCH = 53362688 + 372432640      # profiles/r1_cstr_v7_wsm_ncu_summary.txt
 HEADLINE_INTEGRATOR = {"scheme": "tsit5", "adaptive": False, "n_sub": 1}
 
 
@@ -304,12 +304,12 @@ def main():
                    "parallelism": f"env-sharded x{world}, no collective"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": NCU_DRAM_BYTES_PER_LAUNCH if n == N_ENVS else None,
-                     "traffic_note": "dram__bytes_read+write.sum of one launch, profiles/r1_cstr_v6_mono_ncu_summary.txt "
+                     "traffic_note": "dram__bytes_read+write.sum of one launch, profiles/r1_cstr_v7_wsm_ncu_summary.txt "
                                      "(~55 MB of the stores are still in L2 at kernel end)",
                      "algorithmic_bytes": BYTES_PER_ENV_STEP * env_steps_per_launch,
                      "peak_source": peak_src, "bytes_per_env_step": BYTES_PER_ENV_STEP,
                      "kernel_ms": kern_ms_max, "kernel": kernel_name,
-                     "fp64_note": "FP64-pipe/latency bound, not HBM bound: see profiles/README.md"},
+                     "fp64_note": "instruction-issue / FP64-pipe bound, not HBM bound: ~280 FP64 instructions per env-step against 74 B (profiles/README.md, DESIGN.md section 5)"},
         "cpu_baseline": cpu,
         "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": Ke, "ms_per_step": e2e_ms / Ke},

@@ -108,6 +108,38 @@ def test_rollout_host_pipelined_equals_rollout_bitwise(chunks):
         e2.rollout_host(acts.cuda())
 
 
+def test_three_straight_line_kernels_agree():
+    """The batch size picks the kernel (csrc/launch.cuh): warp-specialised pairs (n = 4 096), persistent CTA per SM with
+    a finisher pool (n = 20 000, last CTA partial), software-pipelined 255-register kernel (n = 70 000).  The first
+    4 096 envs get the same x0 / actions / noise stream in all three, so their outputs must agree to rounding (the
+    integrator warps use a Horner-form exp, the monolithic kernel an Estrin-form one: not bitwise)."""
+    from pcgym_b200 import _native as nat
+    params = cases.cstr_dist_cons()
+    params.pop("disturbances"); params.pop("disturbance_bounds")
+    params.update(noise=True, noise_percentage=0.001, integrator=HEADLINE, seed=21, x0=None)
+    K, m = params["N"] - 1, 4096
+    rng = np.random.default_rng(8)
+    x0 = np.array([0.8, 330.0, 0.8])[None] * (1 + 0.02 * rng.uniform(-1, 1, (70000, 3)))
+    acts = rng.uniform(-1, 1, (K, 1, 70000))
+    outs, kernels = [], []
+    for n in (4096, 20000, 70000):
+        env = _env(dict(params, x0=x0[:n]), n_envs=n)
+        env.reset()
+        out = env.rollout(torch.as_tensor(acts[:, :, :n].copy()))
+        kernels.append(nat.lib().pcg_last_kernel().decode().split(" ")[0])
+        outs.append({k: out[k][..., :m].cpu().numpy().astype(np.float64) for k in ("x", "obs", "reward", "done", "violated")})
+        assert int(env.status.max()) == 0
+    assert kernels == ["ws_rollout_kernel", "wsm_rollout_kernel", "fast_rollout_kernel"], kernels
+    for other in outs[1:]:
+        np.testing.assert_allclose(other["x"], outs[0]["x"], rtol=2e-12, atol=0)
+        np.testing.assert_allclose(other["obs"], outs[0]["obs"], rtol=0, atol=1e-10)
+        ok = outs[0]["violated"] == other["violated"]           # a constraint value within rounding of 0 may flip
+        assert ok.mean() > 0.9999
+        np.testing.assert_allclose(other["reward"][ok], outs[0]["reward"][ok], rtol=1e-9, atol=1e-12)
+        assert np.array_equal(other["done"], outs[0]["done"])
+    assert np.array_equal(outs[1]["x"], outs[0]["x"])             # same integrator code in both warp-specialised kernels
+
+
 # ----------------------------------------------------------------------------- golden do-mpc trajectories through CUDA
 @pytest.mark.parametrize("model", ["cstr", "four_tank", "multistage_extraction", "crystallization", "biofilm_reactor"])
 def test_golden_trajectories_cuda(model, golden_dir):
