@@ -79,9 +79,10 @@ struct FirstOrder {
   struct Aux {};
   PCG_DEV static void prep(const P&, const double*, Aux&) {}
   PCG_HD static constexpr int dpar(int i) { constexpr int t[] = {0}; return t[i]; }
-  static constexpr int EPT = 2, MIN_BLOCKS = 8, MIN_BLOCKS_EPT1 = 8, WS = 1;
+  // WS = 0: measured with the warp-specialised kernels the trivial RHS leaves the integrator warps idle and the
+  // finishers carry everything: 0.142 ms against 0.118 ms (65 536 envs), 41.8 % against 60.8 % of HBM (1 M envs)
+  static constexpr int EPT = 2, MIN_BLOCKS = 8, MIN_BLOCKS_EPT1 = 8, WS = 0;
   static constexpr bool FAST = true;
-  using WsModel = FirstOrder;
   PCG_DEV static void rhs(const P& p, const Aux&, const double* x, const double* u, double* dx) {
     dx[0] = fma(p.K, u[0], -x[0]) * p.inv_tau;                   // :322
   }
