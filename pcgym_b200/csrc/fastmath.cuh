@@ -97,6 +97,23 @@ PCG_DEV double exp_sat_horner(double x) {
   return p * __hiloint2double((n + 1023) << 20, 0);
 }
 
+// Horner form with the 2^n scaling done by an integer add into the exponent field of the polynomial value (one
+// integer instruction instead of a move and a DMUL).  p is in [0.70, 1.42] and |n| <= 1000, so the sum stays a
+// normal number.  NOT NaN-preserving on its own: a NaN argument can come back finite.  Only for right-hand sides
+// whose NaN state re-enters the derivative through another term (cstr: T and ca both appear linearly as well).
+PCG_DEV double exp_sat_horner_iscale(double x) {
+  const double t = fma(x, kMC.log2e, kMC.shift);
+  int n = __double2loint(t);
+  const double nf = t - kMC.shift;
+  double r = fma(nf, kMC.ln2_hi, x);
+  r = fma(nf, kMC.ln2_lo, r);
+  n = max(-1000, min(1000, n));
+  double p = kMC.ex[10];
+#pragma unroll
+  for (int i = 9; i >= 0; --i) p = fma(p, r, kMC.ex[i]);
+  return __hiloint2double(__double2hiint(p) + (n << 20), __double2loint(p));
+}
+
 // ln(u) for a positive NORMAL double (the Box-Muller argument is (k + 1/2) 2^-53, never 0 or denormal).
 // u = m 2^e with m in [sqrt(1/2), sqrt(2)); ln m = 2 atanh(s), s = (m-1)/(m+1), |s| <= 0.1716;
 // odd series to s^19 (remainder < 2e-16), Estrin form.

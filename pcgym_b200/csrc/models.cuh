@@ -64,7 +64,8 @@ struct CstrH : Cstr {
   using WsModel = CstrH;
   PCG_DEV static void rhs(const P& p, const Aux& a, const double* x, const double*, double* dx) {
     const double ca = x[0], T = x[1];
-    const double rate = exp_sat_horner(fma(p.neg_ear, rcp_nr(T), p.ln_k0)) * ca;
+    // a NaN T or ca still reaches dx through the linear terms below, so the status check cannot miss it
+    const double rate = exp_sat_horner_iscale(fma(p.neg_ear, rcp_nr(T), p.ln_k0)) * ca;
     dx[0] = fma(-p.thru, ca, a.feed_c) - rate;
     dx[1] = fma(p.c_heat, rate, fma(p.c_T, T, a.heat0));
   }

@@ -166,6 +166,9 @@ ws_rollout_kernel(const __grid_constant__ pcg_desc d, const __grid_constant__ pc
   uint8_t* pv = io.violated + env0;
 
   // g = G [x; uk] + h, dense; rows >= n_con are zero-filled by the host so they can never flag
+  bool con_u = false;
+#pragma unroll
+  for (int c = 0; c < kFastNcon; ++c) con_u = con_u || d.con_mask_u[c] != 0;
   auto constraints = [&](const double (&xs)[EPT][NX], const double (&uk)[EPT][NUK], double* gout, bool (&viol)[EPT]) {
 #pragma unroll
     for (int e = 0; e < EPT; ++e) viol[e] = false;
@@ -177,8 +180,10 @@ ws_rollout_kernel(const __grid_constant__ pcg_desc d, const __grid_constant__ pc
         double acc = d.con_h[c];
 #pragma unroll
         for (int i = 0; i < NX; ++i) acc = fma(d.con_gx[c][i], xs[e][i], acc);
+        if (con_u) {                                     // uniform: most constraints read states only
 #pragma unroll
-        for (int i = 0; i < NUK; ++i) acc = fma(d.con_gu[c][i], uk[e][i], acc);
+          for (int i = 0; i < NUK; ++i) acc = fma(d.con_gu[c][i], uk[e][i], acc);
+        }
         g[e] = acc;
         viol[e] = viol[e] || (acc > 0.0);
       }

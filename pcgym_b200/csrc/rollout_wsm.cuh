@@ -135,6 +135,9 @@ wsm_rollout_kernel(const __grid_constant__ pcg_desc d, const __grid_constant__ p
   // (addresses in the finisher are 32-bit element indices off the array bases -- one IMAD.WIDE each; wsm_ok()
   // checks that every array of the launch has fewer than 2^31 elements)
   const uint32_t n32 = static_cast<uint32_t>(n);
+  bool con_u = false;
+#pragma unroll
+  for (int c = 0; c < kFastNcon; ++c) con_u = con_u || d.con_mask_u[c] != 0;
   auto constraints = [&](const double (&xs)[EPT][NX], const double (&uk)[EPT][NUK], double* gout, uint32_t gidx,
                          bool (&viol)[EPT]) {
 #pragma unroll
@@ -147,8 +150,10 @@ wsm_rollout_kernel(const __grid_constant__ pcg_desc d, const __grid_constant__ p
         double acc = d.con_h[c];
 #pragma unroll
         for (int i = 0; i < NX; ++i) acc = fma(d.con_gx[c][i], xs[e][i], acc);
+        if (con_u) {                                     // uniform: most constraints read states only
 #pragma unroll
-        for (int i = 0; i < NUK; ++i) acc = fma(d.con_gu[c][i], uk[e][i], acc);
+          for (int i = 0; i < NUK; ++i) acc = fma(d.con_gu[c][i], uk[e][i], acc);
+        }
         g[e] = acc;
         viol[e] = viol[e] || (acc > 0.0);
       }
