@@ -108,6 +108,32 @@ def test_rollout_host_pipelined_equals_rollout_bitwise(chunks):
         e2.rollout_host(acts.cuda())
 
 
+@pytest.mark.parametrize("n", [4096, 20000, 66000])        # pair-per-CTA, per-SM finisher pool (partial CTA), monolithic
+def test_split_rollouts_equal_one_rollout_bitwise(n):
+    """A K-interval rollout cut at arbitrary points (1, 2, 5, 8, 9 intervals: below / at / above the ring depth of the
+    warp-specialised kernels, t0 > 0) reproduces the single launch bit for bit, including the sticky done flag and
+    cons_info rows."""
+    params = cases.cstr_dist_cons()
+    params.pop("disturbances"); params.pop("disturbance_bounds")
+    params.update(noise=True, noise_percentage=0.001, integrator=HEADLINE, seed=3)
+    K = params["N"] - 1
+    rng = np.random.default_rng(12)
+    acts = torch.as_tensor(rng.uniform(-1, 1, (K, 1, n))).cuda()
+    one, many = _env(params, n_envs=n), _env(params, n_envs=n)
+    one.reset(); many.reset()
+    ref = one.rollout(acts)
+    cuts, k0 = [1, 2, 5, 8, 9], 0
+    parts = []
+    for c in cuts + [K - sum(cuts)]:
+        out = many.rollout(acts[k0:k0 + c])
+        parts.append({k: v.clone() for k, v in out.items() if v is not None})
+        k0 += c
+    for key in ("x", "obs", "reward", "done", "violated"):
+        assert same(torch.cat([p[key] for p in parts]).double(), ref[key].double()), key
+    assert same(one.info["cons_info"], many.info["cons_info"]) and same(one._x, many._x)
+    assert torch.equal(one._done_state, many._done_state) and bool(one._done_state.all())
+
+
 def test_three_straight_line_kernels_agree():
     """The batch size picks the kernel (csrc/launch.cuh): warp-specialised pairs (n = 4 096), persistent CTA per SM with
     a finisher pool (n = 20 000, last CTA partial), software-pipelined 255-register kernel (n = 70 000).  The first
