@@ -5,8 +5,8 @@
 // that (a) cost issue slots and (b) split basic blocks, so the two environments a thread carries cannot
 // be interleaved by the scheduler.  These versions are straight-line code with a few ulp of error -- far
 // inside the 1e-6 parity budget -- and they propagate NaN so a diverged environment still reaches the
-// status check.  Polynomial coefficients live in __constant__ memory: DFMA reads them as c[3][..]
-// operands instead of spending two UMOVs per 64-bit immediate.
+// status check.  Polynomial coefficients live in __constant__ memory: one LDC / LDCU per 64-bit constant (sm_100
+// SASS has no constant-bank operands on FP64 instructions) instead of two UMOVs per 64-bit immediate.
 #pragma once
 
 namespace pcg {

@@ -3,6 +3,7 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <cstdlib>
 
 #include "rollout_wsm.cuh"
@@ -115,12 +116,9 @@ inline int ws_override() {
 // keeps 3-4 light warps per scheduler and wins when the batch fills the SMs evenly or thinly (<= 6 pairs of 64
 // envs per SM) and again from ~10 pairs per SM up (16 resident warps against the monolithic kernel's 8); in
 // between (the 7th and 8th pair land two-deep on two of the four schedulers) the 255-register kernel is ahead.
+inline int sm_count();
 inline bool ws_preferred(int64_t n_env) {
-  static const int sms = [] {
-    int dev = 0, v = 148;
-    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
-    return v > 0 ? v : 148;
-  }();
+  const int sms = sm_count();
   const double pairs_per_sm = static_cast<double>(n_env) / (64.0 * sms);
   return pairs_per_sm <= 6.0 || pairs_per_sm > 8.5;
 }
@@ -146,13 +144,16 @@ cudaError_t launch_ws(const pcg_desc& d0, const pcg_io& io, int64_t n_env, int t
 }
 
 // persistent CTA per SM with a dynamically balanced finisher pool (rollout_wsm.cuh)
-inline int sm_count() {
-  static const int sms = [] {
-    int dev = 0, v = 148;
-    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
-    return v > 0 ? v : 148;
-  }();
-  return sms;
+inline int sm_count() {                      // of the calling thread's current device (cached per ordinal)
+  static std::atomic<int> cache[64] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  int v = cache[dev & 63].load(std::memory_order_relaxed);
+  if (v == 0) {
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+    cache[dev & 63].store(v, std::memory_order_relaxed);
+  }
+  return v;
 }
 
 // eligible when every SM gets 2..8 tiles of 64 envs and `done` cannot depend on earlier violations
@@ -175,11 +176,18 @@ inline bool wsm_ok(const pcg_desc& d, const pcg_io& io, int64_t n_env, int64_t k
 template <class M, class TB, int NOISE>
 cudaError_t launch_wsm_n(const pcg_desc& d, const pcg_io& io, const Derived<M, TB>& dv, int64_t n_env, int t0,
                          int k_steps, cudaStream_t s, int64_t epc, int n_tiles) {
-  // > 48 KB of dynamic shared memory needs the opt-in, once per kernel instantiation
-  static const cudaError_t attr = cudaFuncSetAttribute(wsm_rollout_kernel<M, TB, NOISE>,
-                                                       cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                       static_cast<int>(sizeof(WsmShared<M>)));
-  if (attr != cudaSuccess) return attr;
+  // > 48 KB of dynamic shared memory needs the opt-in, once per kernel instantiation AND device
+  static std::atomic<uint64_t> opted{0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) dev = 0;
+  const uint64_t bit = uint64_t{1} << (dev & 63);
+  if (!(opted.load(std::memory_order_acquire) & bit)) {
+    const cudaError_t attr = cudaFuncSetAttribute(wsm_rollout_kernel<M, TB, NOISE>,
+                                                  cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                  static_cast<int>(sizeof(WsmShared<M>)));
+    if (attr != cudaSuccess) return attr;
+    opted.fetch_or(bit, std::memory_order_release);
+  }
   const unsigned grid = static_cast<unsigned>((n_env + epc - 1) / epc);
   wsm_rollout_kernel<M, TB, NOISE><<<grid, 32 * kWsmWarps, sizeof(WsmShared<M>), s>>>(d, io, dv, n_env, t0, k_steps,
                                                                                         epc, n_tiles);

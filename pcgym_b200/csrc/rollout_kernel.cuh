@@ -14,7 +14,8 @@
 //     +25 % DFMA throughput at this occupancy, tools/fp64_microbench.cu) and turn every global access
 //     into a 128-bit one (lane L owns envs 2L, 2L+1: a warp touches 512 contiguous bytes per row).
 //   * Everything uniform lives in the constant bank: the descriptor, the model's derived constants and
-//     the h-scaled Butcher coefficients are kernel parameters, so DFMA reads them as c[0][..] operands.
+//     the h-scaled Butcher coefficients are kernel parameters (one LDCU / LDC per use into a uniform or vector
+//     register; sm_100 has no constant-bank operands on FP64 instructions), never recomputed per thread.
 //   * GENERAL = false drops the rarely used observation slots (observed disturbances, uncertain-parameter
 //     tail, > 2 setpoints, constraints that read them) from the instruction stream.
 //   * Streamed inputs of step k+1 are loaded before step k is integrated; outputs use evict-first stores.
@@ -439,7 +440,7 @@ rollout_kernel(const __grid_constant__ pcg_desc d, const __grid_constant__ pcg_i
       }
 
     // ---- constraint evaluator over state' = [x | sp | dslot | tail] and uk; g > 0 = violated.
-    // Fully unrolled over the constraint index so G and h are direct constant-bank operands.
+    // Fully unrolled over the constraint index so G and h are loaded from fixed constant-bank offsets.
     auto constraints = [&](const double (&sps)[NSPM][EPT], double* gout, bool (&viol)[EPT]) {
 #pragma unroll
       for (int e = 0; e < EPT; ++e) viol[e] = false;

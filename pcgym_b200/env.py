@@ -512,6 +512,7 @@ class make_env:
             for k, v in self._theta_user.items():
                 self._theta[self._theta_names.index(k)] = torch.from_numpy(v).to(dev)
         self._bufs = {}
+        self._trunc = None
         self._pipe = None
         self._a_step = z(1, self._a_lo.shape[0], n)
         self._o_lo = torch.from_numpy(self.observation_space_base.low.astype(np.float64)).to(dev)
@@ -654,17 +655,20 @@ class make_env:
         if self._copy_outputs or self._host_reward:
             obs_soa, r = obs_soa.clone(), r.clone()
         if self._host_reward:
-            r, obs_soa = self._custom_reward(obs_soa, self._a_step[0], a_save_old, t_old, violated.bool(), numpy_in)
+            r, obs_soa = self._custom_reward(obs_soa, self._a_step[0], a_save_old, t_old, violated.view(torch.bool), numpy_in)
         self._last_obs = obs_soa
         self.info["obs"] = obs_soa.T
-        self.info["violated"] = violated.bool()
+        self.info["violated"] = violated.view(torch.bool).clone() if self._copy_outputs else violated.view(torch.bool)
         self.info["status"] = self._status
         if n == 1 and numpy_in:
             self.done = bool(done.item())
             return self._single(obs_soa), float(r.item()) if isinstance(r, torch.Tensor) else float(r), self.done, False, self.info
-        done_b = done.bool()
+        # the kernel writes 0 / 1 bytes: reinterpreting them as bool costs no launch
+        done_b = done.view(torch.bool).clone() if self._copy_outputs else done.view(torch.bool)
         self.done = done_b
-        return obs_soa.T, r, done_b, torch.zeros_like(done_b), self.info
+        if self._trunc is None:
+            self._trunc = torch.zeros(n, dtype=torch.bool, device=self.device)
+        return obs_soa.T, r, done_b, self._trunc, self.info
 
     def _uk(self, a_soa, a_save_old, t_old):
         """Physical input vector uk [Nu, n] of the interval just integrated (pcgym.py:372-414), for custom rewards."""
