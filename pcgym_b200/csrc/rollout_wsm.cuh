@@ -41,9 +41,10 @@ wsm_rollout_kernel(const __grid_constant__ pcg_desc d, const __grid_constant__ p
   const int64_t cta_end = (cta_base + envs_per_cta < n) ? cta_base + envs_per_cta : n;
 
   // lanes that own envs in tile p (the last tile of a CTA may be partial; envs_per_cta and n are even)
+  const int cta_pairs = static_cast<int>((cta_end - cta_base) / 2);            // env pairs (= lanes) this CTA owns
   auto tile_lanes = [&](int p) {
-    const int64_t left = (cta_end - (cta_base + static_cast<int64_t>(p) * 64)) / 2;
-    return left < 0 ? 0 : (left > 32 ? 32 : static_cast<int>(left));
+    const int left = cta_pairs - p * 32;
+    return left < 0 ? 0 : (left > 32 ? 32 : left);
   };
   if (warp < n_tiles && lane == 0) {
     const int cnt = tile_lanes(warp) > 0 ? tile_lanes(warp) : 1;
@@ -202,13 +203,15 @@ wsm_rollout_kernel(const __grid_constant__ pcg_desc d, const __grid_constant__ p
 
   // ---- task loop
   const int n_tasks = k_steps * n_tiles;
+  // floor(q / n_tiles) = umulhi(q, ceil(2^32 / n_tiles)) for q < 2^32 / n_tiles (n_tiles <= 8, q < 2^27: launch.cuh)
+  const uint32_t tiles_rcp = static_cast<uint32_t>((uint64_t{1} << 32) / static_cast<uint32_t>(n_tiles)) + 1u;
 #pragma unroll 1
   while (true) {
     int q = 0;
     if (lane == 0) q = atomicAdd(&sh.next_task, 1);
     q = __shfl_sync(0xffffffffu, q, 0);
     if (q >= n_tasks) break;
-    const int k = q / n_tiles, p = q - k * n_tiles;
+    const int k = static_cast<int>(__umulhi(static_cast<uint32_t>(q), tiles_rcp)), p = q - k * n_tiles;   // q / n_tiles
     if (lane >= tile_lanes(p)) continue;
     WsPair<M>& sp = sh.tile[p];
     const int s = k & (R - 1);
