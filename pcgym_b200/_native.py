@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libpcgym_b200.so")
+LIB_PATH = os.environ.get("PCG_LIB") or os.path.join(HERE, "libpcgym_b200.so")     # PCG_LIB: A/B profiling knob
 
 ABI_VERSION = 2
 MAX_NX, MAX_NU, MAX_NSP, MAX_ND, MAX_NTAIL, MAX_NCON, MAX_PARAM = 24, 8, 4, 4, 8, 8, 32
