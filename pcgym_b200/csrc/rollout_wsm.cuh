@@ -28,7 +28,7 @@ struct WsmShared {
   int next_task;
 };
 
-template <class M, class TB, int NOISE>
+template <class M, class TB, int NOISE, int NSP>   // NSP = number of setpoints (1 or 2): no dead lanes of reward / SP work
 __global__ void __launch_bounds__(32 * kWsmWarps, 1)
 wsm_rollout_kernel(const __grid_constant__ pcg_desc d, const __grid_constant__ pcg_io io,
                    const __grid_constant__ Derived<M, TB> dv, const int64_t n, const int t0, const int k_steps,
@@ -227,12 +227,11 @@ wsm_rollout_kernel(const __grid_constant__ pcg_desc d, const __grid_constant__ p
     for (int j = 0; j < NU; ++j) ld_row<EPT>(io.a + ((k_pre * NU + j) * n32 + env0), a_pre[j]);
 
     // SP[t] (shown in the observation) and SP[t+1] (enters the reward)
-    double spc[kFastNsp][EPT], spn[kFastNsp][EPT];
+    double spc[NSP][EPT], spn[NSP][EPT];
     const uint32_t sp_st = static_cast<uint32_t>(io.sp_st), sp_se = static_cast<uint32_t>(io.sp_se);
 #pragma unroll
-    for (int j = 0; j < kFastNsp; ++j) {
-      const uint32_t jj = j < nsp ? j : 0;
-      const uint32_t si = jj * static_cast<uint32_t>(io.sp_sj) + env0 * sp_se + static_cast<uint32_t>(t) * sp_st;
+    for (int j = 0; j < NSP; ++j) {
+      const uint32_t si = j * static_cast<uint32_t>(io.sp_sj) + env0 * sp_se + static_cast<uint32_t>(t) * sp_st;
 #pragma unroll
       for (int e = 0; e < EPT; ++e) {
         spc[j][e] = io.sp[si + e * sp_se];
@@ -297,10 +296,10 @@ wsm_rollout_kernel(const __grid_constant__ pcg_desc d, const __grid_constant__ p
       done[e] = done0[e] || last;                                              // done_on_cons_vio is off (launcher)
       double acc = 0.0;
 #pragma unroll
-      for (int j = 0; j < kFastNsp; ++j) {                                     // r_scale[j >= nsp] == 0
+      for (int j = 0; j < NSP; ++j) {
         const double err = pick<NX>(xe[e], d.sp_state[j]) - spn[j][e];
         acc = fma(-(err * err), d.r_scale[j], acc);                            // pcgym.py:555
-        acc -= (violated[e] && j < nsp) ? pen : 0.0;                           // once per SP key (pcgym.py:556)
+        acc -= violated[e] ? pen : 0.0;                                        // once per SP key (pcgym.py:556)
       }
       r[e] = acc;
     }
@@ -318,7 +317,7 @@ wsm_rollout_kernel(const __grid_constant__ pcg_desc d, const __grid_constant__ p
       st_row<EPT>(io.obs + (io_ + i * n32), w);
     }
 #pragma unroll
-    for (int j = 0; j < kFastNsp; ++j) {
+    for (int j = 0; j < NSP; ++j) {
       double w[EPT];
 #pragma unroll
       for (int e = 0; e < EPT; ++e) w[e] = fma(spc[j][e], d.o_scale[NX + j], d.o_off[NX + j]);
