@@ -173,7 +173,7 @@ inline bool wsm_ok(const pcg_desc& d, const pcg_io& io, int64_t n_env, int64_t k
   return tiles >= 2 && tiles < kWsmMaxTiles;       // 8 tiles per SM: the 255-register kernel is ahead (profiles/)
 }
 
-template <class M, class TB, int NOISE, int NSP>
+template <class M, class TB, int NOISE, int NSP, bool CONU>
 cudaError_t launch_wsm_n(const pcg_desc& d, const pcg_io& io, const Derived<M, TB>& dv, int64_t n_env, int t0,
                          int k_steps, cudaStream_t s, int64_t epc, int n_tiles) {
   // > 48 KB of dynamic shared memory needs the opt-in, once per kernel instantiation AND device
@@ -182,25 +182,28 @@ cudaError_t launch_wsm_n(const pcg_desc& d, const pcg_io& io, const Derived<M, T
   if (cudaGetDevice(&dev) != cudaSuccess) dev = 0;
   const uint64_t bit = uint64_t{1} << (dev & 63);
   if (!(opted.load(std::memory_order_acquire) & bit)) {
-    const cudaError_t attr = cudaFuncSetAttribute(wsm_rollout_kernel<M, TB, NOISE, NSP>,
+    const cudaError_t attr = cudaFuncSetAttribute(wsm_rollout_kernel<M, TB, NOISE, NSP, CONU>,
                                                   cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                   static_cast<int>(sizeof(WsmShared<M>)));
     if (attr != cudaSuccess) return attr;
     opted.fetch_or(bit, std::memory_order_release);
   }
   const unsigned grid = static_cast<unsigned>((n_env + epc - 1) / epc);
-  wsm_rollout_kernel<M, TB, NOISE, NSP><<<grid, 32 * kWsmWarps, sizeof(WsmShared<M>), s>>>(d, io, dv, n_env, t0,
+  wsm_rollout_kernel<M, TB, NOISE, NSP, CONU><<<grid, 32 * kWsmWarps, sizeof(WsmShared<M>), s>>>(d, io, dv, n_env, t0,
                                                                                              k_steps, epc, n_tiles);
   return cudaGetLastError();
 }
 
-template <class M, class TB, int NSP>
+template <class M, class TB, int NSP, bool CONU>
 cudaError_t launch_wsm_s(const pcg_desc& d, const pcg_io& io, const Derived<M, TB>& dv, int64_t n_env, int t0,
                          int k_steps, cudaStream_t s, int64_t epc, int n_tiles) {
   switch (d.noise) {
-    case PCG_NOISE_OFF: return launch_wsm_n<M, TB, PCG_NOISE_OFF, NSP>(d, io, dv, n_env, t0, k_steps, s, epc, n_tiles);
-    case PCG_NOISE_PHILOX: return launch_wsm_n<M, TB, PCG_NOISE_PHILOX, NSP>(d, io, dv, n_env, t0, k_steps, s, epc, n_tiles);
-    default: return launch_wsm_n<M, TB, PCG_NOISE_PHILOX_F32, NSP>(d, io, dv, n_env, t0, k_steps, s, epc, n_tiles);
+    case PCG_NOISE_OFF:
+      return launch_wsm_n<M, TB, PCG_NOISE_OFF, NSP, CONU>(d, io, dv, n_env, t0, k_steps, s, epc, n_tiles);
+    case PCG_NOISE_PHILOX:
+      return launch_wsm_n<M, TB, PCG_NOISE_PHILOX, NSP, CONU>(d, io, dv, n_env, t0, k_steps, s, epc, n_tiles);
+    default:
+      return launch_wsm_n<M, TB, PCG_NOISE_PHILOX_F32, NSP, CONU>(d, io, dv, n_env, t0, k_steps, s, epc, n_tiles);
   }
 }
 
@@ -209,8 +212,15 @@ cudaError_t launch_wsm(const pcg_desc& d0, const pcg_io& io, int64_t n_env, int 
                        int64_t epc, int n_tiles) {
   const pcg_desc d = fold_desc<M>(d0);
   const Derived<M, TB> dv = make_derived<M, TB>(d);
-  const cudaError_t e = d.nsp == 1 ? launch_wsm_s<M, TB, 1>(d, io, dv, n_env, t0, k_steps, s, epc, n_tiles)
-                                   : launch_wsm_s<M, TB, 2>(d, io, dv, n_env, t0, k_steps, s, epc, n_tiles);
+  bool con_u = false;                       // does any constraint read an input column?
+  for (int c = 0; c < d.n_con; ++c) con_u = con_u || d.con_mask_u[c] != 0;
+  cudaError_t e;
+  if (d.nsp == 1)
+    e = con_u ? launch_wsm_s<M, TB, 1, true>(d, io, dv, n_env, t0, k_steps, s, epc, n_tiles)
+              : launch_wsm_s<M, TB, 1, false>(d, io, dv, n_env, t0, k_steps, s, epc, n_tiles);
+  else
+    e = con_u ? launch_wsm_s<M, TB, 2, true>(d, io, dv, n_env, t0, k_steps, s, epc, n_tiles)
+              : launch_wsm_s<M, TB, 2, false>(d, io, dv, n_env, t0, k_steps, s, epc, n_tiles);
   t_last_kernel = "wsm_rollout_kernel (persistent CTA per SM: integrator warps + finisher pool)";
   return e;
 }

@@ -28,7 +28,9 @@ struct WsmShared {
   int next_task;
 };
 
-template <class M, class TB, int NOISE, int NSP>   // NSP = number of setpoints (1 or 2): no dead lanes of reward / SP work
+// NSP = number of setpoints (1 or 2), CONU = some constraint reads an input: compile-time, so the finisher carries
+// no dead reward / setpoint / input-column work and no branch for it
+template <class M, class TB, int NOISE, int NSP, bool CONU>
 __global__ void __launch_bounds__(32 * kWsmWarps, 1)
 wsm_rollout_kernel(const __grid_constant__ pcg_desc d, const __grid_constant__ pcg_io io,
                    const __grid_constant__ Derived<M, TB> dv, const int64_t n, const int t0, const int k_steps,
@@ -136,9 +138,6 @@ wsm_rollout_kernel(const __grid_constant__ pcg_desc d, const __grid_constant__ p
   // (addresses in the finisher are 32-bit element indices off the array bases -- one IMAD.WIDE each; wsm_ok()
   // checks that every array of the launch has fewer than 2^31 elements)
   const uint32_t n32 = static_cast<uint32_t>(n);
-  bool con_u = false;
-#pragma unroll
-  for (int c = 0; c < kFastNcon; ++c) con_u = con_u || d.con_mask_u[c] != 0;
   auto constraints = [&](const double (&xs)[EPT][NX], const double (&uk)[EPT][NUK], double* gout, uint32_t gidx,
                          bool (&viol)[EPT]) {
 #pragma unroll
@@ -151,7 +150,7 @@ wsm_rollout_kernel(const __grid_constant__ pcg_desc d, const __grid_constant__ p
         double acc = d.con_h[c];
 #pragma unroll
         for (int i = 0; i < NX; ++i) acc = fma(d.con_gx[c][i], xs[e][i], acc);
-        if (con_u) {                                     // uniform: most constraints read states only
+        if constexpr (CONU) {                            // most constraints read states only
 #pragma unroll
           for (int i = 0; i < NUK; ++i) acc = fma(d.con_gu[c][i], uk[e][i], acc);
         }
@@ -271,20 +270,23 @@ wsm_rollout_kernel(const __grid_constant__ pcg_desc d, const __grid_constant__ p
     // (written in the prologue before the tile's ring was released: ordered by the full_a -> full_x chain)
     const uchar2 d0 = sh.done0[p][lane];
     const bool done0[EPT] = {d0.x != 0, d0.y != 0};
-    double xe[EPT][NX], a_raw[NU][EPT], uk[EPT][NUK];
+    double xe[EPT][NX], uk[EPT][NUK];
 #pragma unroll
     for (int i = 0; i < NX; ++i) {
       const double2 v = sp.x[s][i][lane];
       xe[0][i] = v.x;
       xe[1][i] = v.y;
     }
+    if constexpr (CONU) {                                   // the input vector is only needed by such constraints
+      double a_raw[NU][EPT];
 #pragma unroll
-    for (int j = 0; j < NU; ++j) {
-      const double2 v = sp.a[s][j][lane];
-      a_raw[j][0] = v.x;
-      a_raw[j][1] = v.y;
+      for (int j = 0; j < NU; ++j) {
+        const double2 v = sp.a[s][j][lane];
+        a_raw[j][0] = v.x;
+        a_raw[j][1] = v.y;
+      }
+      to_uk(a_raw, uk);
     }
-    to_uk(a_raw, uk);
 
     const uint32_t row = kn + env0;                                            // element [k][env0] of the [K][n] arrays
     bool violated[EPT], done[EPT];
