@@ -40,7 +40,7 @@ K_STEPS = N_HORIZON - 1
 # SURVEY 8(d) quotes 82 B because it assumes per-env setpoint tensors (8 B more read per env-step); the
 # headline uses the reference's shared setpoint schedule, which costs no per-env traffic.
 BYTES_PER_ENV_STEP = 74
-NCU_DRAM_BYTES_PER_LAUNCH = 53362688 + 372432640      # profiles/r1_cstr_v7_wsm_ncu_summary.txt
+NCU_DRAM_BYTES_PER_LAUNCH = 53310208 + 371888640      # profiles/r1_cstr_v8_wsm_ncu_summary.txt
 HEADLINE_INTEGRATOR = {"scheme": "tsit5", "adaptive": False, "n_sub": 1}
 
 
@@ -304,7 +304,7 @@ def main():
                    "parallelism": f"env-sharded x{world}, no collective"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": NCU_DRAM_BYTES_PER_LAUNCH if n == N_ENVS else None,
-                     "traffic_note": "dram__bytes_read+write.sum of one launch, profiles/r1_cstr_v7_wsm_ncu_summary.txt "
+                     "traffic_note": "dram__bytes_read+write.sum of one launch, profiles/r1_cstr_v8_wsm_ncu_summary.txt "
                                      "(~55 MB of the stores are still in L2 at kernel end)",
                      "algorithmic_bytes": BYTES_PER_ENV_STEP * env_steps_per_launch,
                      "peak_source": peak_src, "bytes_per_env_step": BYTES_PER_ENV_STEP,
