@@ -190,8 +190,10 @@ def main():
         raise SystemExit("bench.py needs a CUDA device (the engine has no CPU fallback)")
     torch.cuda.set_device(local)
     dev = f"cuda:{local}"
+    numa_cpus = []
     if world > 1:
         sharding.init_from_env("nccl")
+        numa_cpus = sharding.bind_to_gpu_numa(local)       # pinned e2e buffers next to this rank's GPU
     n = args.n_envs
     W, K = max(args.warmup, 3), args.steps
 
@@ -301,7 +303,8 @@ def main():
                    "n_envs_per_gpu": n, "intervals_per_launch": K_STEPS, "integrator": HEADLINE_INTEGRATOR,
                    "parity": "rtol 1e-6 vs converged oracle at this size: tests/test_gpu_parity.py::test_headline_config_full_size_rtol_1e6",
                    "l2": "inputs+outputs per launch ~0.48 GB > 126 MB L2; action buffers rotate over a ring of 3",
-                   "parallelism": f"env-sharded x{world}, no collective"},
+                   "parallelism": f"env-sharded x{world}, no collective" +
+                                  (f"; ranks bound to their GPU's NUMA CPUs ({len(numa_cpus)} on rank 0)" if numa_cpus else "")},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": NCU_DRAM_BYTES_PER_LAUNCH if n == N_ENVS else None,
                      "traffic_note": "dram__bytes_read+write.sum of one launch, profiles/r1_cstr_v8_wsm_ncu_summary.txt "

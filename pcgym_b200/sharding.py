@@ -62,6 +62,27 @@ def init_from_env(backend: str | None = None):
     return rank, world, local
 
 
+def bind_to_gpu_numa(local_rank: int) -> list:
+    """Pin this process to the CPUs NVML reports as closest to GPU `local_rank` (its NUMA node), so that pinned
+    host buffers allocated afterwards are first-touched next to the GPU's PCIe root.  With one process per GPU and
+    host<->device copies in the timed region (bench.py `e2e`) this keeps the ranks from sharing one socket's memory
+    controllers.  Returns the CPU list it bound to ([] = left unchanged: NVML unavailable or mask empty)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(int(local_rank))
+        n_words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, n_words)
+        cpus = [64 * w + b for w, word in enumerate(mask) for b in range(64) if (int(word) >> b) & 1]
+        allowed = os.sched_getaffinity(0)
+        cpus = [c for c in cpus if c in allowed]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return cpus
+    except Exception:
+        return []
+
+
 def max_over_ranks(value: float, device=None) -> float:
     """Device-timed durations are reduced with MAX so the slowest rank defines the step time."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
