@@ -41,12 +41,12 @@ PCG_DEV void mbar_wait(uint64_t* b, uint32_t parity) {   // acquire.cta; try_wai
   } while (!ok);
 }
 
-template <class M>
+template <class M, int RING = kWsRing>
 struct WsPair {
-  double2 a[kWsRing][M::NU][32];
-  double2 x[kWsRing][M::NX][32];
-  uint64_t full_a[kWsRing];
-  uint64_t full_x[kWsRing];
+  double2 a[RING][M::NU][32];
+  double2 x[RING][M::NX][32];
+  uint64_t full_a[RING];
+  uint64_t full_x[RING];
 };
 
 template <class M, class TB, int NOISE, int W>

@@ -19,12 +19,18 @@ namespace pcg {
 
 constexpr int kWsmWarps = 16;      // 512 threads, 128 registers: one CTA fills an SM
 constexpr int kWsmMaxTiles = 8;    // integrator warps per CTA (<= 512 envs per SM)
+// Ring depth.  An mbarrier wait names its phase by PARITY only, so a waiter may never be a whole phase ahead of the
+// barrier.  A finisher holding interval k + RING of a tile while interval k of the same tile is still waiting for the
+// integrator would be exactly that; all the intervals in between would be outstanding too, i.e. RING + 1 finishers
+// stuck on one tile.  With RING >= the number of finishers (<= 14) that cannot happen, so no further ordering is
+// needed between finishers (an earlier version with RING = 8 had to serialise tasks per slot with a counter).
+constexpr int kWsmRing = 16;
+static_assert(kWsmRing >= kWsmWarps - 2 && (kWsmRing & (kWsmRing - 1)) == 0, "ring depth vs finisher count");
 
 template <class M>
 struct WsmShared {
-  WsPair<M> tile[kWsmMaxTiles];
+  WsPair<M, kWsmRing> tile[kWsmMaxTiles];
   uchar2 done0[kWsmMaxTiles][32];   // sticky done flag each env entered the launch with
-  int slot_seq[kWsmMaxTiles][kWsRing];   // finished tasks per ring slot (see the task loop)
   int next_task;
 };
 
@@ -35,7 +41,7 @@ __global__ void __launch_bounds__(32 * kWsmWarps, 1)
 wsm_rollout_kernel(const __grid_constant__ pcg_desc d, const __grid_constant__ pcg_io io,
                    const __grid_constant__ Derived<M, TB> dv, const int64_t n, const int t0, const int k_steps,
                    const int64_t envs_per_cta, const int n_tiles) {
-  constexpr int NX = M::NX, NU = M::NU, ND = M::ND, NUK = NU + ND, EPT = 2, R = kWsRing;
+  constexpr int NX = M::NX, NU = M::NU, ND = M::ND, NUK = NU + ND, EPT = 2, R = kWsmRing;
   extern __shared__ __align__(16) unsigned char wsm_raw[];
   WsmShared<M>& sh = *reinterpret_cast<WsmShared<M>*>(wsm_raw);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -57,7 +63,6 @@ wsm_rollout_kernel(const __grid_constant__ pcg_desc d, const __grid_constant__ p
     }
   }
   if (threadIdx.x == 0) sh.next_task = 0;
-  if (threadIdx.x < kWsmMaxTiles * kWsRing) (&sh.slot_seq[0][0])[threadIdx.x] = 0;
   __syncthreads();
 
   auto to_uk = [&](const double (&a_raw)[NU][EPT], double (&uk)[EPT][NUK]) {   // pcgym.py:372-375, 386-414
@@ -73,7 +78,7 @@ wsm_rollout_kernel(const __grid_constant__ pcg_desc d, const __grid_constant__ p
   if (warp < n_tiles) {
     // ================================================================ integrator warp of tile `warp`
     if (lane >= tile_lanes(warp)) return;
-    WsPair<M>& sp = sh.tile[warp];
+    WsPair<M, R>& sp = sh.tile[warp];
     const int64_t env0 = cta_base + static_cast<int64_t>(warp) * 64 + 2 * lane;
     double x[EPT][NX];
 #pragma unroll
@@ -166,7 +171,7 @@ wsm_rollout_kernel(const __grid_constant__ pcg_desc d, const __grid_constant__ p
 #pragma unroll 1
   for (int p = fin; p < n_tiles; p += n_fin) {
     if (lane >= tile_lanes(p)) continue;
-    WsPair<M>& sp = sh.tile[p];
+    WsPair<M, R>& sp = sh.tile[p];
     const int64_t env0 = cta_base + static_cast<int64_t>(p) * 64 + 2 * lane;
     const double* pa = io.a + env0;
     double a0[NU][EPT];
@@ -212,7 +217,7 @@ wsm_rollout_kernel(const __grid_constant__ pcg_desc d, const __grid_constant__ p
     if (q >= n_tasks) break;
     const int k = static_cast<int>(__umulhi(static_cast<uint32_t>(q), tiles_rcp)), p = q - k * n_tiles;   // q / n_tiles
     if (lane >= tile_lanes(p)) continue;
-    WsPair<M>& sp = sh.tile[p];
+    WsPair<M, R>& sp = sh.tile[p];
     const int s = k & (R - 1);
     const int t = t0 + k, t_new = t + 1;                                       // pcgym.py:441
     const uint32_t env0 = static_cast<uint32_t>(cta_base) + static_cast<uint32_t>(p) * 64u + 2u * lane;
@@ -257,15 +262,7 @@ wsm_rollout_kernel(const __grid_constant__ pcg_desc d, const __grid_constant__ p
         }
       }
     }
-    // An mbarrier wait names its phase by PARITY only, so it may look one phase ahead at most; with more finishers
-    // than ring slots per tile a finisher can hold interval k while k - R is still being finished by another one.
-    // slot_seq counts the finished tasks of a slot: wait for the predecessor first, then for the integrator.
     const int c = k / R;
-    if (c > 0) {
-      const volatile int* seq = &sh.slot_seq[p][s];
-      while (*seq < c) __nanosleep(64);
-      __threadfence_block();
-    }
     mbar_wait(&sp.full_x[s], c & 1);
     // (written in the prologue before the tile's ring was released: ordered by the full_a -> full_x chain)
     const uchar2 d0 = sh.done0[p][lane];
@@ -333,14 +330,6 @@ wsm_rollout_kernel(const __grid_constant__ pcg_desc d, const __grid_constant__ p
 #pragma unroll
       for (int j = 0; j < NU; ++j) sp.a[s][j][lane] = make_double2(a_pre[j][0], a_pre[j][1]);
       mbar_arrive(&sp.full_a[s]);
-    }
-    {                                                                          // this slot's task c is finished
-      const int tl = tile_lanes(p);
-      __syncwarp(tl == 32 ? 0xffffffffu : ((1u << tl) - 1u));
-      if (lane == 0) {
-        __threadfence_block();
-        *const_cast<volatile int*>(&sh.slot_seq[p][s]) = c + 1;
-      }
     }
     if (k == k_steps - 1 && io.done_state) {                                   // the sticky flag after this launch
 #pragma unroll
