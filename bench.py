@@ -250,21 +250,26 @@ def main():
     # ---- end-to-end through the public API with HOST buffers (pinned): H2D actions, D2H obs/reward/done
     a_host = [r.cpu().pin_memory() for r in ring[:2]]
     out_host = None
+    out_sets = [None, None]
     def one_e2e(i):
-        # public API with host buffers: actions H2D, kernel(s), obs/reward/done D2H, all inside; complete on return
+        # public API with host buffers: actions H2D, kernel(s), obs/reward/done D2H of THIS step, all enqueued here.
+        # wait=False lets step i+1's upload overlap step i's download (two result sets alternate); env.host_sync()
+        # before the closing barrier completes every step inside the timed region.
         nonlocal out_host
         env.rewind()
-        out_host = env.rollout_host(a_host[i % 2], out=out_host, chunks=args.e2e_chunks)
+        out_sets[i % 2] = out_host = env.rollout_host(a_host[i % 2], out=out_sets[i % 2], chunks=args.e2e_chunks, wait=False)
         return out_host
     Ke = max(3, min(K, 10))
     for i in range(2):
         one_e2e(i)
+    env.host_sync()
     barrier()
     t0 = time.perf_counter()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(Ke):
         one_e2e(i)
+    env.host_sync()                                   # every step's results are in host memory
     e1.record()
     barrier()
     e2e_ms = sharding.max_over_ranks(e0.elapsed_time(e1), dev)

@@ -514,6 +514,7 @@ class make_env:
         self._bufs = {}
         self._trunc = None
         self._pipe = None
+        self._pipe_prev = None
         self._a_step = z(1, self._a_lo.shape[0], n)
         self._o_lo = torch.from_numpy(self.observation_space_base.low.astype(np.float64)).to(dev)
         self._o_hi = torch.from_numpy(self.observation_space_base.high.astype(np.float64)).to(dev)
@@ -560,6 +561,7 @@ class make_env:
     # ------------------------------------------------------------------ reset (pcgym.py:263-349)
     def reset(self, seed: int = 0, **kwargs):
         self._ensure_device()
+        self._join_pipe()
         self.t = 0
         nx, n = self.Nx_oracle, self.n_envs
         x0 = self._x0_dev.clone()
@@ -634,6 +636,7 @@ class make_env:
             raise RuntimeError("call reset() before step()")
         if self.t >= self.N - 1:
             raise IndexError(f"episode finished: t = {self.t}, N = {self.N} (list index out of range)")
+        self._join_pipe()
         n, nu_a = self.n_envs, self._a_lo.shape[0]
         numpy_in = not isinstance(action, torch.Tensor)
         a = torch.as_tensor(np.asarray(action, dtype=np.float64)) if numpy_in else action
@@ -718,6 +721,7 @@ class make_env:
         Returns SoA tensors: obs [K, Nx, n], reward [K, n], done/violated [K, n] (uint8), x [K, nx, n]."""
         if not self._dev_ready:
             raise RuntimeError("call reset() before rollout()")
+        self._join_pipe()
         n, nu_a = self.n_envs, self._a_lo.shape[0]
         a = actions if isinstance(actions, torch.Tensor) else torch.as_tensor(np.asarray(actions, dtype=np.float64))
         if a.ndim != 3:
@@ -740,13 +744,16 @@ class make_env:
                 raise ValueError(f"z must be [K, {self.Nx_oracle}, {n}]")
         return self._launch(a, K, want_x=want_x, z=z)
 
-    def rollout_host(self, actions, out=None, chunks: int = 8, want_x: bool = False):
+    def rollout_host(self, actions, out=None, chunks: int = 8, want_x: bool = False, wait: bool = True):
         """`rollout` for HOST buffers: `actions` [K, nu_a, n_envs] float64 in (ideally pinned) host memory; returns
         pinned host tensors obs [K, Nx, n], reward [K, n], done [K, n] (and x [K, nx, n] if `want_x`), reusing `out`
         when given.  The K intervals are cut into `chunks` time slices -- contiguous in both the action and the
         output layouts -- and pipelined over three streams: the host->device copy of slice c+1 and the
         device->host copy of slice c-1 overlap the kernel of slice c (PCIe is full duplex), so the call costs about
-        max(H2D, D2H) instead of their sum.  The result is complete when the call returns (it synchronises)."""
+        max(H2D, D2H) instead of their sum.  The result is complete when the call returns (it synchronises).
+        With `wait=False` the call only enqueues: successive calls then overlap as well (slice j of the next call waits
+        for the device->host copy of slice j of this one, nothing more), and `host_sync()` must be called before `out`
+        is read -- alternate two `out` sets to keep one readable."""
         if not self._dev_ready:
             raise RuntimeError("call reset() before rollout_host()")
         if self._host_reward:
@@ -773,16 +780,23 @@ class make_env:
         a_dev = self._bufs.get(("a_dev", K))
         if a_dev is None:
             a_dev = self._bufs[("a_dev", K)] = torch.empty(K, nu_a, n, dtype=torch.float64, device=dev)
-        s_in.wait_stream(main)                    # earlier work on the caller's stream may still read a_dev / bufs
-        s_out.wait_stream(main)
-        edges = np.linspace(0, K, max(1, min(int(chunks), K)) + 1).astype(int)
-        for k0, k1 in zip(edges[:-1], edges[1:]):
-            k0, k1 = int(k0), int(k1)
+        edges = [int(e) for e in np.linspace(0, K, max(1, min(int(chunks), K)) + 1).astype(int)]
+        prev = self._pipe_prev if self._pipe_prev is not None and self._pipe_prev[0] == (K, tuple(edges), want_x) else None
+        if prev is None:                          # different slicing (or first call): order behind everything in flight
+            main.wait_stream(s_out)
+            s_in.wait_stream(main)
+            s_out.wait_stream(main)
+        ev_ks, ev_outs = [], []
+        for j, (k0, k1) in enumerate(zip(edges[:-1], edges[1:])):
             with torch.cuda.stream(s_in):
+                if prev is not None:
+                    s_in.wait_event(prev[1][j])   # the previous call's kernel has finished reading this action slice
                 a_dev[k0:k1].copy_(a[k0:k1], non_blocking=True)
                 ev_in = torch.cuda.Event()
                 ev_in.record(s_in)
             main.wait_event(ev_in)
+            if prev is not None:
+                main.wait_event(prev[2][j])       # ... and its results have left this output slice
             self._launch(a_dev[k0:k1], k1 - k0, want_x, bufs={k: (v[k0:k1] if v is not None else None) for k, v in bufs.items()})
             ev_k = torch.cuda.Event()
             ev_k.record(main)
@@ -790,9 +804,28 @@ class make_env:
                 s_out.wait_event(ev_k)
                 for k in keys:
                     out[k][k0:k1].copy_(bufs[k][k0:k1], non_blocking=True)
-        main.wait_stream(s_out)
-        torch.cuda.current_stream(dev).synchronize()
+                ev_o = torch.cuda.Event()
+                ev_o.record(s_out)
+            ev_ks.append(ev_k)
+            ev_outs.append(ev_o)
+        self._pipe_prev = ((K, tuple(edges), want_x), ev_ks, ev_outs)
+        if wait:
+            self.host_sync()
         return out
+
+    def _join_pipe(self):
+        """Order the caller's stream behind copies still in flight from rollout_host(wait=False)."""
+        if self._pipe_prev is not None:
+            torch.cuda.current_stream(self.device).wait_stream(self._pipe[1])
+            self._pipe_prev = None
+
+    def host_sync(self):
+        """Complete every `rollout_host(..., wait=False)` issued so far (results are in their `out` buffers)."""
+        if self._pipe is not None:
+            main = torch.cuda.current_stream(self.device)
+            main.wait_stream(self._pipe[1])
+            main.synchronize()
+        self._pipe_prev = None
 
     def _launch(self, a, K, want_x, z=None, bufs=None):
         d = self._desc

@@ -106,6 +106,17 @@ def test_rollout_host_pipelined_equals_rollout_bitwise(chunks):
     assert out2 is out and same(out["obs"], ref["obs"].cpu())
     with pytest.raises(ValueError):
         e2.rollout_host(acts.cuda())
+    # back-to-back calls without waiting: two result sets alternate, host_sync() completes both
+    a2 = torch.as_tensor(rng.uniform(-1, 1, (K, 1, n))).pin_memory()
+    e1.reset(); ref1 = {k: v.clone() for k, v in e1.rollout(acts.cuda()).items() if v is not None}
+    e1.rewind(); ref2 = e1.rollout(a2.cuda())
+    e2.reset()
+    o1 = e2.rollout_host(acts.pin_memory(), chunks=chunks, wait=False)
+    e2.rewind()
+    o2 = e2.rollout_host(a2, chunks=chunks, wait=False)
+    e2.host_sync()
+    assert o1 is not o2 and same(o1["obs"], ref1["obs"].cpu()) and same(o2["obs"], ref2["obs"].cpu())
+    assert same(o2["reward"], ref2["reward"].cpu())
 
 
 @pytest.mark.parametrize("n", [4096, 20000, 66000])        # pair-per-CTA, per-SM finisher pool (partial CTA), monolithic
