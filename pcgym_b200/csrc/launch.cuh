@@ -106,7 +106,8 @@ cudaError_t launch_fast(const pcg_desc& d0, const pcg_io& io, int64_t n_env, int
 }
 
 // warp-specialised kernel (rollout_ws.cuh): models that opt in (M::WS > 0 = pairs per CTA), 128-bit rows.
-// PCG_WS=0 falls back to the monolithic fast kernel, PCG_WS=1|2 picks the pairs per CTA (profiling knobs).
+// PCG_WS=0 forces the monolithic fast kernel, PCG_WS=1 the pair-per-CTA kernel, PCG_WS=3 the per-SM kernel
+// (profiling knobs).
 inline int ws_override() {
   static const int v = [] { const char* e = std::getenv("PCG_WS"); return e ? std::atoi(e) : -1; }();
   return v;
@@ -123,24 +124,32 @@ inline bool ws_preferred(int64_t n_env) {
   return pairs_per_sm <= 6.0 || pairs_per_sm > 8.5;
 }
 
+template <class M, class TB, int W, int NSP>
+cudaError_t launch_ws_s(const pcg_desc& d, const pcg_io& io, const Derived<M, TB>& dv, int64_t n_env, int t0,
+                        int k_steps, cudaStream_t s) {
+  const unsigned grid = static_cast<unsigned>((n_env + 64 * W - 1) / (64 * W));
+  switch (d.noise) {
+    case PCG_NOISE_OFF:
+      ws_rollout_kernel<M, TB, PCG_NOISE_OFF, W, NSP><<<grid, 64 * W, 0, s>>>(d, io, dv, n_env, t0, k_steps);
+      break;
+    case PCG_NOISE_PHILOX:
+      ws_rollout_kernel<M, TB, PCG_NOISE_PHILOX, W, NSP><<<grid, 64 * W, 0, s>>>(d, io, dv, n_env, t0, k_steps);
+      break;
+    default:
+      ws_rollout_kernel<M, TB, PCG_NOISE_PHILOX_F32, W, NSP><<<grid, 64 * W, 0, s>>>(d, io, dv, n_env, t0, k_steps);
+      break;
+  }
+  return cudaGetLastError();
+}
+
 template <class M, class TB, int W>
 cudaError_t launch_ws(const pcg_desc& d0, const pcg_io& io, int64_t n_env, int t0, int k_steps, cudaStream_t s) {
   const pcg_desc d = fold_desc<M>(d0);
-  const unsigned grid = static_cast<unsigned>((n_env + 64 * W - 1) / (64 * W));
   const Derived<M, TB> dv = make_derived<M, TB>(d);
-  switch (d.noise) {
-    case PCG_NOISE_OFF:
-      ws_rollout_kernel<M, TB, PCG_NOISE_OFF, W><<<grid, 64 * W, 0, s>>>(d, io, dv, n_env, t0, k_steps);
-      break;
-    case PCG_NOISE_PHILOX:
-      ws_rollout_kernel<M, TB, PCG_NOISE_PHILOX, W><<<grid, 64 * W, 0, s>>>(d, io, dv, n_env, t0, k_steps);
-      break;
-    default:
-      ws_rollout_kernel<M, TB, PCG_NOISE_PHILOX_F32, W><<<grid, 64 * W, 0, s>>>(d, io, dv, n_env, t0, k_steps);
-      break;
-  }
+  const cudaError_t e = d.nsp == 1 ? launch_ws_s<M, TB, W, 1>(d, io, dv, n_env, t0, k_steps, s)
+                                   : launch_ws_s<M, TB, W, 2>(d, io, dv, n_env, t0, k_steps, s);
   t_last_kernel = "ws_rollout_kernel (warp-specialised integrator/finisher pairs)";
-  return cudaGetLastError();
+  return e;
 }
 
 // persistent CTA per SM with a dynamically balanced finisher pool (rollout_wsm.cuh)
@@ -242,7 +251,6 @@ cudaError_t launch_e(const pcg_desc& d, const pcg_io& io, int64_t n_env, int t0,
           const int w = ws_override() < 0 ? (ws_preferred(n_env) ? M::WS : 0) : ws_override();
           // the integrator warps run the model's WsModel (cstr: Horner-form exp, 3 FP64 issue slots fewer per RHS)
           if (two && w == 1) return launch_ws<typename M::WsModel, TB, 1>(d, io, n_env, t0, k_steps, s);
-          if (two && w == 2) return launch_ws<typename M::WsModel, TB, 2>(d, io, n_env, t0, k_steps, s);
         }
         if (two) return launch_fast<M, TB, 2>(d, io, n_env, t0, k_steps, s);
       }

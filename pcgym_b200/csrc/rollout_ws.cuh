@@ -49,7 +49,8 @@ struct WsPair {
   uint64_t full_x[RING];
 };
 
-template <class M, class TB, int NOISE, int W>
+// NSP = number of setpoints (1 or 2) at compile time: no dead reward / setpoint work (see rollout_wsm.cuh)
+template <class M, class TB, int NOISE, int W, int NSP>
 __global__ void __launch_bounds__(64 * W, W == 1 ? 7 : 3)
 ws_rollout_kernel(const __grid_constant__ pcg_desc d, const __grid_constant__ pcg_io io,
                   const __grid_constant__ Derived<M, TB> dv, const int64_t n, const int t0, const int k_steps) {
@@ -231,12 +232,11 @@ ws_rollout_kernel(const __grid_constant__ pcg_desc d, const __grid_constant__ pc
   }
 
   // setpoint schedule pointers (rows >= nsp alias row 0: loaded, never used)
-  const double* psp[kFastNsp];
-  double sp_cur[kFastNsp][EPT], sp_nxt[kFastNsp][EPT];
+  const double* psp[NSP];
+  double sp_cur[NSP][EPT], sp_nxt[NSP][EPT];
 #pragma unroll
-  for (int j = 0; j < kFastNsp; ++j) {
-    const int jj = j < nsp ? j : 0;
-    psp[j] = io.sp + jj * io.sp_sj + env0 * io.sp_se + static_cast<int64_t>(t0) * io.sp_st;
+  for (int j = 0; j < NSP; ++j) {
+    psp[j] = io.sp + j * io.sp_sj + env0 * io.sp_se + static_cast<int64_t>(t0) * io.sp_st;
 #pragma unroll
     for (int e = 0; e < EPT; ++e) {
       sp_cur[j][e] = psp[j][e * io.sp_se];
@@ -256,9 +256,9 @@ ws_rollout_kernel(const __grid_constant__ pcg_desc d, const __grid_constant__ pc
     for (int j = 0; j < NU; ++j) ld_row<EPT>(pa + j * n, a_pre[j]);
     pa += (k + R + 1 < k_steps) ? static_cast<int64_t>(NU) * n : 0;
 
-    double spc[kFastNsp][EPT], spn[kFastNsp][EPT];           // SP[t] (observation), SP[t+1] (reward)
+    double spc[NSP][EPT], spn[NSP][EPT];           // SP[t] (observation), SP[t+1] (reward)
 #pragma unroll
-    for (int j = 0; j < kFastNsp; ++j) {
+    for (int j = 0; j < NSP; ++j) {
       psp[j] += (t + 2 < d.N) ? io.sp_st : 0;                                  // -> SP[min(t + 2, N - 1)]
 #pragma unroll
       for (int e = 0; e < EPT; ++e) {
@@ -314,10 +314,10 @@ ws_rollout_kernel(const __grid_constant__ pcg_desc d, const __grid_constant__ pc
       done[e] = done[e] || (violated[e] && done_on_v) || last;
       double acc = 0.0;
 #pragma unroll
-      for (int j = 0; j < kFastNsp; ++j) {                                     // r_scale[j >= nsp] == 0
+      for (int j = 0; j < NSP; ++j) {
         const double err = pick<NX>(xe[e], d.sp_state[j]) - spn[j][e];
         acc = fma(-(err * err), d.r_scale[j], acc);                            // pcgym.py:555
-        acc -= (violated[e] && j < nsp) ? pen : 0.0;                           // once per SP key (pcgym.py:556)
+        acc -= violated[e] ? pen : 0.0;                                        // once per SP key (pcgym.py:556)
       }
       r[e] = acc;
     }
@@ -334,7 +334,7 @@ ws_rollout_kernel(const __grid_constant__ pcg_desc d, const __grid_constant__ pc
       st_row<EPT>(po + i * n, w);
     }
 #pragma unroll
-    for (int j = 0; j < kFastNsp; ++j) {
+    for (int j = 0; j < NSP; ++j) {
       double w[EPT];
 #pragma unroll
       for (int e = 0; e < EPT; ++e) w[e] = fma(spc[j][e], d.o_scale[NX + j], d.o_off[NX + j]);
