@@ -217,13 +217,14 @@ PCG_DEV void advance_adaptive(const Derived<M, TB>& dv, const typename M::P& mp,
       for (int i = 0; i < S; ++i)
         if (TB::e(i) != 0.0) err = fma(dv.e[i], hk[i][n], err);
       const double sc = fma(rtol, fmax(fabs(x[n]), fabs(xn[n])), atol);
-      const double r = err / sc;
+      const double r = err * rcp_nr(sc);               // sc > 0 and normal whenever atol > 0 or the state is non-zero
       sq = fma(r, r, sq);
     }
-    const double err = sqrt(sq * (1.0 / NX));
-    const bool finite = isfinite(err);
-    const float grow = finite ? 0.9f * __powf(fmaxf(static_cast<float>(err), 1e-30f), -0.2f) : 0.2f;
-    if (finite && err <= 1.0) {
+    // err = sqrt(sq / NX) is only needed as err <= 1 and err^-1/5 = (sq / NX)^-1/10: no square root
+    const double msq = sq * (1.0 / NX);
+    const bool finite = isfinite(msq);
+    const float grow = finite ? 0.9f * __powf(fmaxf(static_cast<float>(msq), 1e-30f), -0.1f) : 0.2f;
+    if (finite && msq <= 1.0) {
       t = last ? dt : t + hh;
 #pragma unroll
       for (int n = 0; n < NX; ++n) { x[n] = xn[n]; k0[n] = kn[n]; }
