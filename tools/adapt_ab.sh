@@ -1,3 +1,7 @@
+#!/bin/bash
+# same-box A/B of two library builds (pcgym_b200/lib_a.so, lib_b.so) on the ADAPTIVE path: CSTR and
+# multistage_extraction rollouts with adaptive Tsit5; prints ms per launch and RHS evaluations per attempted step / 7
+# (profiling aid)
 for L in pcgym_b200/lib_a.so pcgym_b200/lib_b.so pcgym_b200/lib_a.so pcgym_b200/lib_b.so; do PCG_LIB=$PWD/$L python - <<'PY'
 import sys, os, json, torch
 sys.path.insert(0, '.'); sys.path.insert(0, 'tests')
