@@ -311,6 +311,7 @@ def main():
                    "parallelism": f"env-sharded x{world}, no collective" +
                                   (f"; ranks bound to their GPU's NUMA CPUs ({len(numa_cpus)} on rank 0)" if numa_cpus else "")},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "frac_of_nominal_8000": achieved / 8000.0,
                      "traffic": NCU_DRAM_BYTES_PER_LAUNCH if n == N_ENVS else None,
                      "traffic_note": "dram__bytes_read+write.sum of one launch, profiles/r1_cstr_v8_wsm_ncu_summary.txt "
                                      "(~55 MB of the stores are still in L2 at kernel end)",
