@@ -21,7 +21,10 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 from pcgym_b200 import make_env  # noqa: E402
 import test_gpu_parity as T  # noqa: E402  (reuses the per-model batch scenarios)
 
-CONFIGS = [   # model, n_envs, K, integrator
+CONFIGS = [   # model, n_envs, K, integrator[, measurement noise (default on)]
+    # BASELINE config 2 exactly (noise off, no constraints): the bandwidth sanity case
+    ("first_order_system", 65536, 99, {"scheme": "tsit5", "adaptive": False, "n_sub": 1}, False),
+    ("first_order_system", 1048576, 99, {"scheme": "tsit5", "adaptive": False, "n_sub": 1}, False),
     ("first_order_system", 65536, 99, {"scheme": "tsit5", "adaptive": False, "n_sub": 1}),
     ("first_order_system", 1048576, 99, {"scheme": "tsit5", "adaptive": False, "n_sub": 1}),
     ("cstr", 65536, 99, {"scheme": "tsit5", "adaptive": False, "n_sub": 1}),
@@ -45,9 +48,11 @@ def main():
     args = ap.parse_args()
     peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(
         os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
-    for model, n, K, integ in CONFIGS:
+    for cfg in CONFIGS:
+        model, n, K, integ = cfg[:4]
+        noise = cfg[4] if len(cfg) > 4 else True
         params, x0, acts, key, sp = T.batch_setup(model, n, K)
-        params = dict(params, integrator=integ, noise=True, noise_percentage=0.001)
+        params = dict(params, integrator=integ, noise=noise, noise_percentage=0.001)
         env = make_env(params)
         env.reset()
         a = torch.as_tensor(acts, device="cuda")
@@ -63,7 +68,8 @@ def main():
         b = bytes_per_env_step(env)
         rate = n * K / (ms * 1e-3)
         rhs = float(env.rhs_evaluations.double().mean()) / (K * (args.steps + 3))
-        print(json.dumps({"model": model, "n_envs": n, "intervals": K, "integrator": integ, "ms_per_launch": round(ms, 4),
+        print(json.dumps({"model": model, "n_envs": n, "intervals": K, "integrator": integ, "noise": noise,
+                          "ms_per_launch": round(ms, 4),
                           "env_steps_per_s": rate, "bytes_per_env_step": b, "GBps": rate * b / 1e9,
                           "hbm_frac": rate * b / 1e9 / peak, "rhs_evals_per_interval": round(rhs, 1),
                           "status_nonzero": int((env.status != 0).sum())}), flush=True)
