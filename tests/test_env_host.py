@@ -224,3 +224,52 @@ def test_every_registry_key_of_the_reference_constructs():
     assert (env.Nx_oracle, env.Nx, env.Nu) == (24, 25, 4) and env._desc.model == 11
     with pytest.raises(NotImplementedError):
         models.DeviceModel("coupled_oscillator", N=12)
+
+
+def test_affine_probe_recovers_the_matrices_and_rejects_oversize():
+    from pcgym_b200 import models
+
+    class M:
+        int_method = "casadi"
+        A = np.array([[-1.0, 0.0, 0.5], [0.0, -2.0, 0.0], [1.0, 0.0, -1.0]])
+        B = np.array([[1.0, 0.0], [0.0, 1.0], [0.0, 0.0]])
+        c = np.array([0.1, 0.0, -0.3])
+
+        def __call__(self, x, u):
+            return self.A @ x + self.B @ u + self.c
+
+        def info(self):
+            return {"parameters": {}, "states": ["a", "b", "c"], "inputs": ["p", "q"], "disturbances": []}
+    dm = models.AffineCustomModel(M())
+    np.testing.assert_allclose(dm.A, M.A, atol=1e-15)
+    np.testing.assert_allclose(dm.B, M.B, atol=1e-15)
+    np.testing.assert_allclose(dm.c, M.c, atol=1e-15)
+    assert dm.model_id == nat.AFFINE_BASE + 2 * nat.AFFINE_MAX_NU + 1 and len(dm.theta()) == 9 + 6 + 3
+    assert nat.model_dims(dm.model_id)[:2] == (3, 2)
+
+    class Big(M):
+        def info(self):
+            return {"parameters": {}, "states": list("abcde"), "inputs": ["p"], "disturbances": []}
+    with pytest.raises(NotImplementedError):
+        models.AffineCustomModel(Big())
+
+
+def test_log_table_is_reproducible():
+    """pcgym_b200/csrc/logtab.inc is exactly what tools/gen_logtab.py writes (60-digit decimal arithmetic)."""
+    import os
+    import subprocess
+    import sys
+    import tempfile
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    want = open(os.path.join(root, "pcgym_b200", "csrc", "logtab.inc")).read()
+    src = open(os.path.join(root, "tools", "gen_logtab.py")).read()
+    with tempfile.TemporaryDirectory() as tmp:
+        os.makedirs(os.path.join(tmp, "tools")); os.makedirs(os.path.join(tmp, "pcgym_b200", "csrc"))
+        open(os.path.join(tmp, "tools", "gen_logtab.py"), "w").write(src)
+        subprocess.run([sys.executable, os.path.join(tmp, "tools", "gen_logtab.py")], check=True, capture_output=True)
+        got = open(os.path.join(tmp, "pcgym_b200", "csrc", "logtab.inc")).read()
+    assert got == want
+    rows = [ln for ln in want.splitlines() if ln.startswith("{")]
+    assert len(rows) == 128
+    inv0, m2ln0 = (float.fromhex(v.strip(" {},")) for v in rows[0].split("//")[0].rstrip(",").strip("{}").split(","))
+    assert abs(inv0 - 1 / (1 + 0.5 / 128)) < 1e-16 and abs(m2ln0 + 2 * np.log(1 / inv0)) < 1e-16
