@@ -117,6 +117,7 @@ inline int ws_override() {
 // keeps 3-4 light warps per scheduler and wins when the batch fills the SMs evenly or thinly (<= 6 pairs of 64
 // envs per SM) and again from ~10 pairs per SM up (16 resident warps against the monolithic kernel's 8); in
 // between (the 7th and 8th pair land two-deep on two of the four schedulers) the 255-register kernel is ahead.
+// (Where the per-SM kernel of rollout_wsm.cuh is eligible it is taken before this choice is consulted.)
 inline int sm_count();
 inline bool ws_preferred(int64_t n_env) {
   const int sms = sm_count();
@@ -165,7 +166,8 @@ inline int sm_count() {                      // of the calling thread's current 
   return v;
 }
 
-// eligible when every SM gets 2..8 tiles of 64 envs and `done` cannot depend on earlier violations
+// eligible when every SM gets 2..8 tiles of 64 envs (9.5 k < n <= 75.8 k on 148 SMs) and `done` cannot depend on
+// earlier violations
 inline bool wsm_ok(const pcg_desc& d, const pcg_io& io, int64_t n_env, int64_t k_steps, int64_t* envs_per_cta,
                    int* n_tiles) {
   if (d.flags & PCG_F_DONE_ON_VIOLATION) return false;
@@ -179,7 +181,7 @@ inline bool wsm_ok(const pcg_desc& d, const pcg_io& io, int64_t n_env, int64_t k
   const int tiles = static_cast<int>((epc + 63) / 64);
   *envs_per_cta = epc;
   *n_tiles = tiles;
-  return tiles >= 2 && tiles < kWsmMaxTiles;       // 8 tiles per SM: the 255-register kernel is ahead (profiles/)
+  return tiles >= 2 && tiles <= kWsmMaxTiles;
 }
 
 template <class M, class TB, int NOISE, int NSP, bool CONU>

@@ -119,7 +119,7 @@ def test_rollout_host_pipelined_equals_rollout_bitwise(chunks):
     assert same(o2["reward"], ref2["reward"].cpu())
 
 
-@pytest.mark.parametrize("n", [4096, 20000, 66000])        # pair-per-CTA, per-SM finisher pool (partial CTA), monolithic
+@pytest.mark.parametrize("n", [4096, 20000, 78000])        # pair-per-CTA, per-SM finisher pool (partial CTA), monolithic
 def test_split_rollouts_equal_one_rollout_bitwise(n):
     """A K-interval rollout cut at arbitrary points (1, 2, 5, 8, 9 intervals: below / at / above the ring depth of the
     warp-specialised kernels, t0 > 0) reproduces the single launch bit for bit, including the sticky done flag and
@@ -147,7 +147,7 @@ def test_split_rollouts_equal_one_rollout_bitwise(n):
 
 def test_three_straight_line_kernels_agree():
     """The batch size picks the kernel (csrc/launch.cuh): warp-specialised pairs (n = 4 096), persistent CTA per SM with
-    a finisher pool (n = 20 000, last CTA partial), software-pipelined 255-register kernel (n = 70 000).  The first
+    a finisher pool (n = 20 000, last CTA partial), software-pipelined 255-register kernel (n = 78 000).  The first
     4 096 envs get the same x0 / actions / noise stream in all three, so their outputs must agree to rounding (the
     integrator warps use a Horner-form exp, the monolithic kernel an Estrin-form one: not bitwise)."""
     from pcgym_b200 import _native as nat
@@ -156,10 +156,10 @@ def test_three_straight_line_kernels_agree():
     params.update(noise=True, noise_percentage=0.001, integrator=HEADLINE, seed=21, x0=None)
     K, m = params["N"] - 1, 4096
     rng = np.random.default_rng(8)
-    x0 = np.array([0.8, 330.0, 0.8])[None] * (1 + 0.02 * rng.uniform(-1, 1, (70000, 3)))
-    acts = rng.uniform(-1, 1, (K, 1, 70000))
+    x0 = np.array([0.8, 330.0, 0.8])[None] * (1 + 0.02 * rng.uniform(-1, 1, (78000, 3)))
+    acts = rng.uniform(-1, 1, (K, 1, 78000))
     outs, kernels = [], []
-    for n in (4096, 20000, 70000):
+    for n in (4096, 20000, 78000):
         env = _env(dict(params, x0=x0[:n]), n_envs=n)
         env.reset()
         out = env.rollout(torch.as_tensor(acts[:, :, :n].copy()))

@@ -24,7 +24,7 @@ base = {"model": "cstr", "N": N, "tsim": N * 0.25, "SP": {"Ca": [0.85] * N},
         "constraints": lambda x, u: np.array([319 - x[1], x[1] - 331]).reshape(-1,), "done_on_cons_vio": False,
         "r_penalty": True, "constraint_units": "physical",
         "integrator": {"scheme": "tsit5", "adaptive": False, "n_sub": 1}}
-for n, extra in ((4096 + 2, {}), (20000 + 6, {}), (66500, {}),
+for n, extra in ((4096 + 2, {}), (20000 + 6, {}), (78002, {}),
                  (1001, {"integrator": {"scheme": "tsit5", "adaptive": True, "rtol": 1e-8, "atol": 1e-8}})):
     env = make_env(dict(base, n_envs=n, **extra))
     env.reset()
