@@ -318,7 +318,7 @@ def main():
                      "algorithmic_bytes": BYTES_PER_ENV_STEP * env_steps_per_launch,
                      "peak_source": peak_src, "bytes_per_env_step": BYTES_PER_ENV_STEP,
                      "kernel_ms": kern_ms_max, "kernel": kernel_name,
-                     "fp64_note": "instruction-issue / FP64-pipe bound, not HBM bound: ~280 FP64 instructions per env-step against 74 B (profiles/README.md, DESIGN.md section 5)"},
+                     "fp64_note": "instruction-issue / FP64-pipe bound, not HBM bound: ~250 FP64 + ~225 other instructions per env-step against 74 B (profiles/README.md, DESIGN.md section 5)"},
         "cpu_baseline": cpu,
         "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": Ke, "ms_per_step": e2e_ms / Ke},
