@@ -82,7 +82,7 @@ enum pcg_scheme {
 
 enum pcg_noise {
   PCG_NOISE_OFF = 0,
-  PCG_NOISE_PHILOX = 1,      /* Philox4x32-10 keyed (seed; env, t, lane), fp64 Box-Muller */
+  PCG_NOISE_PHILOX = 1,      /* Philox4x32-10 keyed (seed; env, t, lane), fp64 inverse normal CDF */
   PCG_NOISE_EXTERNAL = 2,    /* standard normals supplied in io.z (parity tests)          */
   PCG_NOISE_PHILOX_F32 = 3   /* same counter scheme, Box-Muller evaluated in fp32         */
 };
@@ -119,6 +119,17 @@ enum pcg_status {
   PCG_E_RANGE = -6,       /* n_env, k_steps, t out of range             */
   PCG_E_ALIGN = -7,       /* fp64 pointer not 8-byte aligned            */
   PCG_E_CUDA = -8         /* CUDA runtime error (pcg_last_cuda_error)   */
+};
+
+/* kernel families (pcg_set_kernel / pcg_last_kernel): csrc/launch.cuh picks one per configuration and batch size */
+enum pcg_kernel {
+  PCG_KERNEL_AUTO = -1,         /* the library's own choice (default)                                            */
+  PCG_KERNEL_GENERIC = 0,       /* rollout_kernel: every option, run-time flags                                  */
+  PCG_KERNEL_FAST = 1,          /* fast_rollout_kernel: straight-line, software-pipelined                        */
+  PCG_KERNEL_WS = 2,            /* ws_rollout_kernel: integrator / finisher warp pairs                           */
+  PCG_KERNEL_WSM = 3,           /* wsm_rollout_kernel: persistent CTA per SM, finisher pool                      */
+  PCG_KERNEL_FAST_EPT1 = 4,     /* fast_rollout_kernel with one environment per thread (64-bit row accesses)    */
+  PCG_KERNEL_GENERIC_EPT1 = 5   /* rollout_kernel with one environment per thread                               */
 };
 
 /* per-env status bits written to io.status */
@@ -246,9 +257,10 @@ int pcg_step(const pcg_desc* d, const pcg_io* io, int64_t n_env, int64_t t, void
 int pcg_rollout(const pcg_desc* d, const pcg_io* io, int64_t n_env, int64_t t0, int64_t k_steps,
                 void* cuda_stream);
 
-/* The measurement-noise transform in isolation (pcgym.py:453-466 draws np.random.normal; here two 32-bit Philox
- * words -> two N(0,1), see csrc/philox.cuh): z0[i], z1[i] from (w0[i], w1[i]) for i < n, device pointers.
- * f32 != 0 selects the PCG_NOISE_PHILOX_F32 evaluation.  Lets a caller check the documented draw exactly. */
+/* The measurement-noise transform in isolation (pcgym.py:453-466 draws np.random.normal; here every 32-bit Philox
+ * word w gives one draw z = Phi^-1((w + 1/2) 2^-32), see csrc/philox.cuh): z0[i] from w0[i] and z1[i] from w1[i]
+ * for i < n, device pointers.  f32 != 0 selects the PCG_NOISE_PHILOX_F32 evaluation (fp32 Box-Muller of the word
+ * pair).  Lets a caller check the documented draw exactly. */
 int pcg_normal_pairs(const uint32_t* w0, const uint32_t* w1, double* z0, double* z1, int64_t n, int f32,
                      void* cuda_stream);
 
@@ -259,6 +271,12 @@ int64_t pcg_launch_count(void);
  * of the most recent failure on the calling thread. */
 const char* pcg_strerror(int status);
 const char* pcg_last_cuda_error(void);
+
+/* Ask for a kernel family for the calling thread's following launches (enum pcg_kernel); returns the previous
+ * request, or PCG_E_RANGE.  A request is honoured only where that family is eligible for the configuration (the usual
+ * fall-back order applies otherwise) -- pcg_last_kernel() tells.  Lets the parity tests drive every instantiation
+ * at every batch size; production code leaves it at PCG_KERNEL_AUTO. */
+int pcg_set_kernel(int kernel);
 
 /* Kernel family the calling thread's most recent pcg_step / pcg_rollout launched (diagnostics: the library
  * picks between the generic, the software-pipelined and the warp-specialised kernel per configuration). */

@@ -14,6 +14,12 @@ parity target (CVODES at its default tolerances is itself only ~1e-5 accurate).
                   (used for batch-sized parity; error ~ (dt/n)^4).
   advance_lsoda   scipy LSODA rtol 1e-6 / atol 1e-8: stand-in for the
                   reference's CVODES defaults, used only for CPU timing.
+  advance_fixed   n_sub steps of a NAMED explicit pair without step control
+                  ("rk4", "dopri5", "tsit5"), vectorised.  The reference's jax
+                  path is diffrax Tsit5 (integrator.py:57); a kernel that takes
+                  one Tsit5 step per control interval is compared with this at
+                  ~1e-12 (same scheme, different arithmetic order) and with the
+                  converged solution at the north-star rtol 1e-6.
 """
 from __future__ import annotations
 
@@ -61,4 +67,54 @@ def advance_dense(model, x, u, dt, p=None, n_sub=64):
         k3 = f(x + (0.5 * h) * k2, u)
         k4 = f(x + h * k3, u)
         x = x + (h / 6.0) * (k1 + 2.0 * k2 + 2.0 * k3 + k4)
+    return x
+
+
+# Butcher tableaus, restated from the literature (NOT parsed from the CUDA sources: tests/test_tableaus.py checks
+# both against the order conditions and against each other).  Rows 1..S-1 are the stage rows, B the solution weights.
+#   rk4    : Kutta 1901.
+#   dopri5 : Dormand & Prince 1980, RK5(4)7M (scipy's "RK45").
+#   tsit5  : Tsitouras 2011, "Runge-Kutta pairs of order 5(4) satisfying only the first column simplifying
+#            assumption" -- the pair diffrax.Tsit5 implements (reference integrator.py:57).
+TABLEAUS = {
+    "rk4": {
+        "A": [[], [1 / 2], [0, 1 / 2], [0, 0, 1]],
+        "B": [1 / 6, 1 / 3, 1 / 3, 1 / 6],
+    },
+    "dopri5": {
+        "A": [[], [1 / 5], [3 / 40, 9 / 40], [44 / 45, -56 / 15, 32 / 9],
+              [19372 / 6561, -25360 / 2187, 64448 / 6561, -212 / 729],
+              [9017 / 3168, -355 / 33, 46732 / 5247, 49 / 176, -5103 / 18656]],
+        "B": [35 / 384, 0, 500 / 1113, 125 / 192, -2187 / 6784, 11 / 84],
+    },
+    "tsit5": {
+        "A": [[], [0.161],
+              [-0.008480655492356989, 0.335480655492357],
+              [2.8971530571054935, -6.359448489975075, 4.3622954328695815],
+              [5.325864828439257, -11.748883564062828, 7.4955393428898365, -0.09249506636175525],
+              [5.86145544294642, -12.92096931784711, 8.159367898576159, -0.071584973281401, -0.028269050394068383]],
+        "B": [0.09646076681806523, 0.01, 0.4798896504144996, 1.379008574103742, -3.290069515436081,
+              2.324710524099774],
+    },
+}
+
+
+def advance_fixed(model, x, u, dt, p=None, scheme="tsit5", n_sub=1):
+    """`n_sub` fixed steps of the explicit scheme, input held: x[nx, N], u[nu, N] -> x[nx, N]."""
+    f = _as_fun(model, p)
+    tb = TABLEAUS[scheme]
+    x = np.array(x, dtype=np.float64)
+    u = np.asarray(u, dtype=np.float64)
+    h = float(dt) / n_sub
+    for _ in range(n_sub):
+        k = []
+        for row in tb["A"]:
+            xi = x.copy()
+            for a, kj in zip(row, k):
+                if a != 0.0:
+                    xi = xi + (h * a) * kj
+            k.append(f(xi, u))
+        for b, kj in zip(tb["B"], k):
+            if b != 0.0:
+                x = x + (h * b) * kj
     return x

@@ -106,7 +106,10 @@ SYMBOLS = {
     "pcg_strerror": (C.c_char_p, [C.c_int]),
     "pcg_last_cuda_error": (C.c_char_p, []),
     "pcg_last_kernel": (C.c_char_p, []),
+    "pcg_set_kernel": (C.c_int, [C.c_int]),
 }
+
+KERNELS = {"auto": -1, "generic": 0, "fast": 1, "ws": 2, "wsm": 3, "fast_ept1": 4, "generic_ept1": 5}
 
 _lib = None
 

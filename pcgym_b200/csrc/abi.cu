@@ -118,8 +118,8 @@ __global__ void normal_pairs_kernel(const uint32_t* w0, const uint32_t* w1, doub
   const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= n) return;
   double a, b;
-  if (f32) pcg::normal_pair_u32<true>(w0[i], w1[i], a, b);
-  else pcg::normal_pair_u32<false>(w0[i], w1[i], a, b);
+  if (f32) pcg::normal_pair_u32<true>(w0[i], w1[i], pcg::kIcdfTab, a, b);
+  else pcg::normal_pair_u32<false>(w0[i], w1[i], pcg::kIcdfTab, a, b);
   z0[i] = a;
   z1[i] = b;
 }
@@ -153,7 +153,8 @@ int validate(const pcg_desc* d, const pcg_io* io, int64_t n_env, int64_t t0, int
   if (adaptive ? (d->max_steps < 1 || !(d->rtol > 0.0) || !(d->atol >= 0.0)) : (d->n_sub < 1)) return PCG_E_RANGE;
   if (!(d->dt > 0.0) || d->N < 2) return PCG_E_RANGE;
   if (n_env < 1 || n_env > (int64_t{1} << 31) - pcg::kBlock || k_steps < 1 || k_steps > (1 << 24)) return PCG_E_RANGE;
-  if (t0 < 0 || t0 + k_steps > (int64_t{1} << 30)) return PCG_E_RANGE;
+  // the kernels read SP / disturbance row t + 1 and write cons_info row t + 1 of every interval: t0 + k_steps <= N - 1
+  if (t0 < 0 || t0 + k_steps > static_cast<int64_t>(d->N) - 1) return PCG_E_RANGE;
   if (!io->x || !io->a) return PCG_E_NULL;
   if (d->nsp > 0 && !io->sp) return PCG_E_NULL;
   if (d->nd > 0) {
@@ -257,5 +258,12 @@ const char* pcg_strerror(int status) {
 const char* pcg_last_cuda_error(void) { return t_cuda_err; }
 
 const char* pcg_last_kernel(void) { return pcg::t_last_kernel; }
+
+int pcg_set_kernel(int kernel) {
+  if (kernel < PCG_KERNEL_AUTO || kernel > PCG_KERNEL_GENERIC_EPT1) return PCG_E_RANGE;
+  const int prev = pcg::t_kernel_request;
+  pcg::t_kernel_request = kernel;
+  return prev;
+}
 
 }  // extern "C"

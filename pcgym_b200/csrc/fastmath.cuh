@@ -1,4 +1,4 @@
-// Branch-free fp64 helpers for the RHS hot loops and the Gaussian draws.
+// Branch-free fp64 helpers for the RHS hot loops.
 //
 // The rollout kernels are bound by the FP64 pipe and, at 65 536 envs, by dependent-issue latency
 // (profiles/).  The CUDA library exp()/log()/sincospi()/division carry special-case branches
@@ -19,9 +19,6 @@ namespace pcg {
 struct MathConst {
   double log2e, ln2_hi, ln2_lo, shift;
   double ex[11];      // exp(r) on |r| <= ln2/2: degree-10 interpolant at Chebyshev nodes, max rel. error 4.4e-16
-  double at[10];      // 2/(2k+1): ln m = s * sum at[k] s^2k,  s = (m-1)/(m+1)
-  double sn[8];       // sin(pi x)/x   in x^2, |x| <= 1/4
-  double cs[8];       // cos(pi x)     in x^2
 };
 
 static __constant__ MathConst kMC = {
@@ -29,10 +26,6 @@ static __constant__ MathConst kMC = {
     {1.0, 1.0000000000000067, 0.5000000000000006, 0.16666666666554325, 0.04166666666657431, 0.008333333385696902,
      0.0013888888932304278, 0.0001984117023243583, 2.4801504458882045e-05, 2.764019693014132e-06,
      2.762633679135001e-07},
-    {2.0, 2.0 / 3, 2.0 / 5, 2.0 / 7, 2.0 / 9, 2.0 / 11, 2.0 / 13, 2.0 / 15, 2.0 / 17, 2.0 / 19},
-    // Taylor coefficients of sin(pi x)/x and cos(pi x) in x^2: (-1)^k pi^(2k+1)/(2k+1)!, (-1)^k pi^(2k)/(2k)!
-    {3.141592653589793, -5.167712780049969, 2.550164039877345, -0.5992645293207919, 0.08214588661112819, -0.007370430945714348, 0.00046630280576761234, -2.1915353447830204e-05},
-    {1.0, -4.934802200544679, 4.058712126416768, -1.3352627688545893, 0.23533063035889312, -0.02580689139001405, 0.001929574309403922, -0.00010463810492484565},
 };
 
 // 1/a: MUFU.RCP64H seed (2^-23) + two Newton steps -> ~1 ulp for normal a.
@@ -45,18 +38,14 @@ PCG_DEV double rcp_nr(double a) {
   return fma(r, e, r);
 }
 
-// sqrt(a) for a > 0: MUFU.RSQ64H seed + Newton on y = 1/sqrt(a), then one correction of a*y.
-PCG_DEV double sqrt_nr(double a) {
-  double y;
-  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
-  double h = 0.5 * y;
-  double e = fma(-a * y, h, 0.5);          // 1/2 - a y^2 / 2
-  y = fma(y, e, y);
-  h = 0.5 * y;
-  e = fma(-a * y, h, 0.5);
-  y = fma(y, e, y);
-  const double s = a * y;
-  return fma(fma(-s, s, a), 0.5 * y, s);
+// n = rint(x log2 e) read back from the shifted double t = x log2 e + 1.5*2^52, clamped to +-1000.  The mantissa of t
+// holds n as a 52-bit two's-complement integer; its low word alone wraps for |n| >= 2^31 (a hugely negative argument
+// would come back with a positive n), so the high word decides: it equals the sign extension of the low word exactly
+// when n fits 32 bits, and its own sign gives the saturation side otherwise.
+PCG_DEV int exp_n_sat(double t) {
+  const int lo = __double2loint(t), hd = __double2hiint(t) - 0x43380000;
+  const int n = (hd == (lo >> 31)) ? lo : (hd < 0 ? -1000 : 1000);
+  return max(-1000, min(1000, n));
 }
 
 // exp(x), saturating at 2^+-1000 instead of overflowing, NaN-propagating.
@@ -64,11 +53,10 @@ PCG_DEV double sqrt_nr(double a) {
 // in Estrin form (dependency depth 4 instead of Horner's 10), scaled by 2^n built in the exponent field.
 PCG_DEV double exp_sat(double x) {
   const double t = fma(x, kMC.log2e, kMC.shift);
-  int n = __double2loint(t);
+  const int n = exp_n_sat(t);
   const double nf = t - kMC.shift;
   double r = fma(nf, kMC.ln2_hi, x);
   r = fma(nf, kMC.ln2_lo, r);
-  n = max(-1000, min(1000, n));
   const double r2 = r * r, r4 = r2 * r2, r8 = r4 * r4;
   const double a0 = fma(kMC.ex[1], r, kMC.ex[0]);
   const double a1 = fma(kMC.ex[3], r, kMC.ex[2]);
@@ -86,11 +74,10 @@ PCG_DEV double exp_sat(double x) {
 // Three FP64 issue slots cheaper per call; used where other warps hide the longer dependency chain.
 PCG_DEV double exp_sat_horner(double x) {
   const double t = fma(x, kMC.log2e, kMC.shift);
-  int n = __double2loint(t);
+  const int n = exp_n_sat(t);
   const double nf = t - kMC.shift;
   double r = fma(nf, kMC.ln2_hi, x);
   r = fma(nf, kMC.ln2_lo, r);
-  n = max(-1000, min(1000, n));
   double p = kMC.ex[10];
 #pragma unroll
   for (int i = 9; i >= 0; --i) p = fma(p, r, kMC.ex[i]);
@@ -103,60 +90,52 @@ PCG_DEV double exp_sat_horner(double x) {
 // whose NaN state re-enters the derivative through another term (cstr: T and ca both appear linearly as well).
 PCG_DEV double exp_sat_horner_iscale(double x) {
   const double t = fma(x, kMC.log2e, kMC.shift);
-  int n = __double2loint(t);
+  const int n = exp_n_sat(t);
   const double nf = t - kMC.shift;
   double r = fma(nf, kMC.ln2_hi, x);
   r = fma(nf, kMC.ln2_lo, r);
-  n = max(-1000, min(1000, n));
   double p = kMC.ex[10];
 #pragma unroll
   for (int i = 9; i >= 0; --i) p = fma(p, r, kMC.ex[i]);
   return __hiloint2double(__double2hiint(p) + (n << 20), __double2loint(p));
 }
 
-// ln(u) for a positive NORMAL double (the Box-Muller argument is (k + 1/2) 2^-53, never 0 or denormal).
-// u = m 2^e with m in [sqrt(1/2), sqrt(2)); ln m = 2 atanh(s), s = (m-1)/(m+1), |s| <= 0.1716;
-// odd series to s^19 (remainder < 2e-16), Estrin form.
-PCG_DEV double log_pos(double u) {
-  int hi = __double2hiint(u);
-  const int lo = __double2loint(u);
-  int e = (hi >> 20) - 1023;
-  hi = (hi & 0x000fffff) | 0x3ff00000;              // m in [1, 2)
-  const bool big = hi >= 0x3ff6a09f;                // m >= sqrt(2) (to 20 bits): halve it
-  hi = big ? hi - 0x00100000 : hi;
-  e = big ? e + 1 : e;
-  const double m = __hiloint2double(hi, lo);
-  const double s = (m - 1.0) * rcp_nr(m + 1.0);
-  const double z = s * s, z2 = z * z, z4 = z2 * z2;
-  const double a0 = fma(kMC.at[1], z, kMC.at[0]);
-  const double a1 = fma(kMC.at[3], z, kMC.at[2]);
-  const double a2 = fma(kMC.at[5], z, kMC.at[4]);
-  const double a3 = fma(kMC.at[7], z, kMC.at[6]);
-  const double a4 = fma(kMC.at[9], z, kMC.at[8]);
-  const double b0 = fma(a1, z2, a0);
-  const double b1 = fma(a3, z2, a2);
-  const double p = fma(fma(a4, z4, b1), z4, b0);
-  const double ef = static_cast<double>(e);
-  return fma(ef, -kMC.ln2_hi, fma(s, p, ef * -kMC.ln2_lo));
+// 1/a with ONE third-order correction of the MUFU.RCP64H seed (relative error e <= 2^-23):
+// r (1 + e + e^2) = (1/a)(1 - e^3), i.e. 2^-69 before rounding -- three dependent DFMA instead of rcp_nr's four.
+PCG_DEV double rcp_o3(double a) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(a));
+  const double e = fma(-a, r, 1.0);
+  return fma(fma(r, e, r), e, r);
 }
 
-// sin(pi v), cos(pi v) for v in [0, 2): quadrant reduction to |x| <= 1/4, degree-15/14 Taylor in x (remainder 1e-15).
-PCG_DEV void sincospi_02(double v, double& s, double& c) {
-  const double q = rint(v * 2.0);                   // nearest half-integer count, 0..4
-  const double x = fma(q, -0.5, v);                 // |x| <= 1/4 exactly representable reduction
-  const int k = static_cast<int>(q);
-  const double z = x * x;
-  double ps = kMC.sn[7], pc = kMC.cs[7];
-#pragma unroll
-  for (int i = 6; i >= 0; --i) {
-    ps = fma(ps, z, kMC.sn[i]);
-    pc = fma(pc, z, kMC.cs[i]);
-  }
-  ps *= x;
-  const bool swap = k & 1;
-  const double ss = swap ? pc : ps, cc = swap ? ps : pc;
-  s = (k & 2) ? -ss : ss;                           // k=0: (s,c)  1: (c,-s)  2: (-s,-c)  3: (-c,s)  4: (s,c)
-  c = ((k + 1) & 2) ? -cc : cc;
+// Table-driven exp for the integrator warps of the warp-specialised kernels (the serial part of the rollout, where
+// both the FP64 instruction count and the LENGTH of the dependency chain set the pace):
+//   n = rint(256 x log2 e) by the 1.5*2^52 shift, x = (n >> 8) ln2 + (n & 255) ln2/256 + r,  |r| <= ln2/512,
+//   exp(x) = 2^(n >> 8) * 2^((n & 255)/256) * (1 + r + r^2/2 + r^3/6 + r^4/24)        (remainder r^5/120 < 4e-17)
+// Eight FP64 instructions and a dependency depth of 7 against 14 / 13 for exp_sat_horner.  The reduction uses ln2/256
+// as ONE constant: its rounding error times n is ~|x| 0.8e-16 relative in the result, the size of the rounding
+// error x itself carries.  `tab` is a shared-memory copy of kExp2Tab.  Returned in two factors so the caller can
+// fold its own multiplier into `scale` while the polynomial is still in flight: exp(x) = scale * poly.
+// Saturates at 2^+-1000 for |256 x log2 e| < 2^39 (the shifted double holds n as a 52-bit two's-complement integer;
+// bits 8..39 are used), NaN-propagating (poly is NaN).
+struct ExpTabConst { double l256, nln2_256, shift, c2, c3, c4; };
+static __constant__ ExpTabConst kET = {369.3299304675746, -0.0027076061740622863, 6755399441055744.0,
+                                       0.5, 1.0 / 6, 1.0 / 24};
+static __device__ const double kExp2Tab[256] = {
+#include "exp2tab.inc"
+};
+
+PCG_DEV void exp_tab_split(double x, const double* tab, double& scale, double& poly) {
+  const double t = fma(x, kET.l256, kET.shift);
+  const int lo = __double2loint(t), hd = __double2hiint(t) - 0x43380000;
+  const double nf = t - kET.shift;
+  const double r = fma(nf, kET.nln2_256, x);
+  int m = __funnelshift_r(lo, hd, 8);
+  m = max(-1000, min(1000, m));
+  const double tj = tab[lo & 255];
+  scale = __hiloint2double(__double2hiint(tj) + (m << 20), __double2loint(tj));
+  poly = fma(fma(fma(fma(kET.c4, r, kET.c3), r, kET.c2), r, 1.0), r, 1.0);
 }
 
 }  // namespace pcg

@@ -63,8 +63,7 @@ inline bool fast_ok(const pcg_desc& d, const pcg_io& io) {
   if (d.noise == PCG_NOISE_EXTERNAL) return false;
   if (!io.x_traj || !io.obs || !io.reward || !io.done || !io.violated) return false;
   if (d.n_con > 0 && !io.g) return false;
-  static const bool off = std::getenv("PCG_NO_FAST") != nullptr;               // profiling knob
-  return !off;
+  return true;
 }
 
 // The straight-line kernels apply every option arithmetically: the descriptor they see has the options folded
@@ -184,38 +183,48 @@ inline bool wsm_ok(const pcg_desc& d, const pcg_io& io, int64_t n_env, int64_t k
   return tiles >= 2 && tiles <= kWsmMaxTiles;
 }
 
-template <class M, class TB, int NOISE, int NSP, bool CONU>
+template <class M, class TB, int NOISE, int NSP, bool CONU, bool SPS>
 cudaError_t launch_wsm_n(const pcg_desc& d, const pcg_io& io, const Derived<M, TB>& dv, int64_t n_env, int t0,
                          int k_steps, cudaStream_t s, int64_t epc, int n_tiles) {
+  using Shared = WsmShared<M, NOISE, NSP, SPS>;
   // > 48 KB of dynamic shared memory needs the opt-in, once per kernel instantiation AND device
   static std::atomic<uint64_t> opted{0};
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) dev = 0;
   const uint64_t bit = uint64_t{1} << (dev & 63);
   if (!(opted.load(std::memory_order_acquire) & bit)) {
-    const cudaError_t attr = cudaFuncSetAttribute(wsm_rollout_kernel<M, TB, NOISE, NSP, CONU>,
+    const cudaError_t attr = cudaFuncSetAttribute(wsm_rollout_kernel<M, TB, NOISE, NSP, CONU, SPS>,
                                                   cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                  static_cast<int>(sizeof(WsmShared<M>)));
+                                                  static_cast<int>(sizeof(Shared)));
     if (attr != cudaSuccess) return attr;
     opted.fetch_or(bit, std::memory_order_release);
   }
   const unsigned grid = static_cast<unsigned>((n_env + epc - 1) / epc);
-  wsm_rollout_kernel<M, TB, NOISE, NSP, CONU><<<grid, 32 * kWsmWarps, sizeof(WsmShared<M>), s>>>(d, io, dv, n_env, t0,
-                                                                                             k_steps, epc, n_tiles);
+  wsm_rollout_kernel<M, TB, NOISE, NSP, CONU, SPS><<<grid, 32 * kWsmWarps, sizeof(Shared), s>>>(d, io, dv, n_env, t0,
+                                                                                            k_steps, epc, n_tiles);
   return cudaGetLastError();
 }
 
-template <class M, class TB, int NSP, bool CONU>
+template <class M, class TB, int NSP, bool CONU, bool SPS>
 cudaError_t launch_wsm_s(const pcg_desc& d, const pcg_io& io, const Derived<M, TB>& dv, int64_t n_env, int t0,
                          int k_steps, cudaStream_t s, int64_t epc, int n_tiles) {
   switch (d.noise) {
     case PCG_NOISE_OFF:
-      return launch_wsm_n<M, TB, PCG_NOISE_OFF, NSP, CONU>(d, io, dv, n_env, t0, k_steps, s, epc, n_tiles);
+      return launch_wsm_n<M, TB, PCG_NOISE_OFF, NSP, CONU, SPS>(d, io, dv, n_env, t0, k_steps, s, epc, n_tiles);
     case PCG_NOISE_PHILOX:
-      return launch_wsm_n<M, TB, PCG_NOISE_PHILOX, NSP, CONU>(d, io, dv, n_env, t0, k_steps, s, epc, n_tiles);
+      return launch_wsm_n<M, TB, PCG_NOISE_PHILOX, NSP, CONU, SPS>(d, io, dv, n_env, t0, k_steps, s, epc, n_tiles);
     default:
-      return launch_wsm_n<M, TB, PCG_NOISE_PHILOX_F32, NSP, CONU>(d, io, dv, n_env, t0, k_steps, s, epc, n_tiles);
+      return launch_wsm_n<M, TB, PCG_NOISE_PHILOX_F32, NSP, CONU, SPS>(d, io, dv, n_env, t0, k_steps, s, epc, n_tiles);
   }
+}
+
+template <class M, class TB, int NSP, bool CONU>
+cudaError_t launch_wsm_c(const pcg_desc& d, const pcg_io& io, const Derived<M, TB>& dv, int64_t n_env, int t0,
+                         int k_steps, cudaStream_t s, int64_t epc, int n_tiles) {
+  // the reference's setpoints are ONE schedule for every env (SP[k][t], pcgym.py:432-438): staged in shared memory
+  const bool sps = io.sp_se == 0 && k_steps + 1 <= kWsmSpMax;
+  return sps ? launch_wsm_s<M, TB, NSP, CONU, true>(d, io, dv, n_env, t0, k_steps, s, epc, n_tiles)
+             : launch_wsm_s<M, TB, NSP, CONU, false>(d, io, dv, n_env, t0, k_steps, s, epc, n_tiles);
 }
 
 template <class M, class TB>
@@ -227,32 +236,54 @@ cudaError_t launch_wsm(const pcg_desc& d0, const pcg_io& io, int64_t n_env, int 
   for (int c = 0; c < d.n_con; ++c) con_u = con_u || d.con_mask_u[c] != 0;
   cudaError_t e;
   if (d.nsp == 1)
-    e = con_u ? launch_wsm_s<M, TB, 1, true>(d, io, dv, n_env, t0, k_steps, s, epc, n_tiles)
-              : launch_wsm_s<M, TB, 1, false>(d, io, dv, n_env, t0, k_steps, s, epc, n_tiles);
+    e = con_u ? launch_wsm_c<M, TB, 1, true>(d, io, dv, n_env, t0, k_steps, s, epc, n_tiles)
+              : launch_wsm_c<M, TB, 1, false>(d, io, dv, n_env, t0, k_steps, s, epc, n_tiles);
   else
-    e = con_u ? launch_wsm_s<M, TB, 2, true>(d, io, dv, n_env, t0, k_steps, s, epc, n_tiles)
-              : launch_wsm_s<M, TB, 2, false>(d, io, dv, n_env, t0, k_steps, s, epc, n_tiles);
+    e = con_u ? launch_wsm_c<M, TB, 2, true>(d, io, dv, n_env, t0, k_steps, s, epc, n_tiles)
+              : launch_wsm_c<M, TB, 2, false>(d, io, dv, n_env, t0, k_steps, s, epc, n_tiles);
   t_last_kernel = "wsm_rollout_kernel (persistent CTA per SM: integrator warps + finisher pool)";
   return e;
 }
 
+// Kernel-family request of the calling thread (pcg_set_kernel; PCG_KERNEL_AUTO = the library's own choice).  A request
+// is honoured only where that family is eligible; otherwise the usual fall-back order applies, and pcg_last_kernel()
+// says what actually ran.  The environment knobs PCG_WS (0 fast, 1 pair-per-CTA, 3 per-SM), PCG_WSM=0, PCG_NO_FAST and
+// PCG_EPT=1 give the process-wide default (profiling aids).
+inline thread_local int t_kernel_request = PCG_KERNEL_AUTO;
+inline int kernel_request() {
+  if (t_kernel_request != PCG_KERNEL_AUTO) return t_kernel_request;
+  static const int env = [] {
+    if (std::getenv("PCG_NO_FAST")) return static_cast<int>(PCG_KERNEL_GENERIC);
+    switch (ws_override()) {
+      case 0: return static_cast<int>(PCG_KERNEL_FAST);
+      case 1: return static_cast<int>(PCG_KERNEL_WS);
+      case 3: return static_cast<int>(PCG_KERNEL_WSM);
+    }
+    return static_cast<int>(PCG_KERNEL_AUTO);
+  }();
+  return env;
+}
+
 template <class M, class TB, bool ADAPTIVE, bool GENERAL>
 cudaError_t launch_e(const pcg_desc& d, const pcg_io& io, int64_t n_env, int t0, int k_steps, cudaStream_t s) {
+  const int req = kernel_request();
+  const bool ept1 = ept_override() == 1 || req == PCG_KERNEL_FAST_EPT1 || req == PCG_KERNEL_GENERIC_EPT1;
   // two envs per thread share one Philox block, which needs an even global id for the first of them
-  const bool two = M::EPT == 2 && ept_override() != 1 && vector_ok(io, n_env) && d.env_id0 % 2 == 0;
+  const bool two = M::EPT == 2 && !ept1 && vector_ok(io, n_env) && d.env_id0 % 2 == 0;
+  const bool generic = req == PCG_KERNEL_GENERIC || req == PCG_KERNEL_GENERIC_EPT1;
   if constexpr (!ADAPTIVE && !GENERAL && M::FAST) {
-    if (fast_ok<M>(d, io)) {
+    if (!generic && fast_ok<M>(d, io)) {
       if constexpr (M::EPT == 2) {
         if constexpr (M::WS > 0) {
-          // PCG_WS=3 forces / PCG_WSM=0 forbids the per-SM kernel (profiling knobs)
           static const bool wsm_off = [] { const char* e = std::getenv("PCG_WSM"); return e && std::atoi(e) == 0; }();
           int64_t epc = 0;
           int tiles = 0;
-          if (two && wsm_ok(d, io, n_env, k_steps, &epc, &tiles) && (ws_override() == 3 || (ws_override() < 0 && !wsm_off)))
+          if (two && wsm_ok(d, io, n_env, k_steps, &epc, &tiles) &&
+              (req == PCG_KERNEL_WSM || (req == PCG_KERNEL_AUTO && !wsm_off)))
             return launch_wsm<typename M::WsModel, TB>(d, io, n_env, t0, k_steps, s, epc, tiles);
-          const int w = ws_override() < 0 ? (ws_preferred(n_env) ? M::WS : 0) : ws_override();
-          // the integrator warps run the model's WsModel (cstr: Horner-form exp, 3 FP64 issue slots fewer per RHS)
-          if (two && w == 1) return launch_ws<typename M::WsModel, TB, 1>(d, io, n_env, t0, k_steps, s);
+          const bool ws = req == PCG_KERNEL_WS || ((req == PCG_KERNEL_AUTO || req == PCG_KERNEL_WSM) && ws_preferred(n_env));
+          // the integrator warps run the model's WsModel (cstr: table-driven exp, 8 FP64 issue slots fewer per RHS)
+          if (two && ws) return launch_ws<typename M::WsModel, TB, 1>(d, io, n_env, t0, k_steps, s);
         }
         if (two) return launch_fast<M, TB, 2>(d, io, n_env, t0, k_steps, s);
       }

@@ -25,6 +25,9 @@ namespace pcg {
 // ---------------------------------------------------------------------------------------
 // cstr -- model_classes.py:23-62
 // theta: q V rho C deltaHr EA_over_R k0 UA Ti Caf       disturbances: Ti, Caf
+#ifndef PCG_CSTR_WSMODEL
+#define PCG_CSTR_WSMODEL CstrT
+#endif
 struct Cstr {
   static constexpr int NX = 2, NU = 1, ND = 2, NP = 10;
   struct P { double thru, ln_k0, neg_ear, c_heat, c_cool, c_T; };
@@ -50,7 +53,7 @@ struct Cstr {
   static constexpr int MIN_BLOCKS = 4, MIN_BLOCKS_EPT1 = 7;   // 7 x 64 threads x 144 regs: 65 536 envs in one wave
   static constexpr bool FAST = true;              // has straight-line kernel instantiations (rollout_fast / rollout_ws)
   static constexpr int WS = 1;                    // warp-specialised kernel: integrator/finisher pairs per CTA
-  using WsModel = struct CstrH;                   // RHS variant its integrator warps run
+  using WsModel = struct PCG_CSTR_WSMODEL;        // RHS variant its integrator warps run (CstrT; -DPCG_CSTR_WSMODEL=CstrH: A/B)
   PCG_DEV static void rhs(const P& p, const Aux& a, const double* x, const double*, double* dx) {
     const double ca = x[0], T = x[1];
     const double rate = exp_sat(fma(p.neg_ear, rcp_nr(T), p.ln_k0)) * ca;        // :52
@@ -68,6 +71,28 @@ struct CstrH : Cstr {
     const double rate = exp_sat_horner_iscale(fma(p.neg_ear, rcp_nr(T), p.ln_k0)) * ca;
     dx[0] = fma(-p.thru, ca, a.feed_c) - rate;
     dx[1] = fma(p.c_heat, rate, fma(p.c_T, T, a.heat0));
+  }
+};
+
+// cstr as the integrator warps of the warp-specialised kernels run it: table-driven exponential (exp_tab_split, 8 FP64
+// instructions, dependency depth 7) and the third-order reciprocal (3 DFMA): 17 FP64 instructions + 1 MUFU per RHS
+// against 25 for CstrH, and a dependency chain about half as long.  The Arrhenius factor comes back as scale * poly;
+// scale * ca and c_heat * scale * ca are formed while the polynomial is in flight, so the derivative is one DFMA behind it.
+struct CstrT : Cstr {
+  using WsModel = CstrT;
+  static constexpr bool EXP_TAB = true;           // Aux carries the shared-memory 2^(j/256) table (kExp2Tab)
+  struct Aux { double feed_c, heat0; const double* tab; };
+  PCG_DEV static void prep(const P& p, const double* u, Aux& a) {
+    a.feed_c = p.thru * u[2];
+    a.heat0 = fma(p.thru, u[1], p.c_cool * u[0]);
+  }
+  PCG_DEV static void rhs(const P& p, const Aux& a, const double* x, const double*, double* dx) {
+    const double ca = x[0], T = x[1];
+    double scale, poly;
+    exp_tab_split(fma(p.neg_ear, rcp_o3(T), p.ln_k0), a.tab, scale, poly);       // :52  k0 exp(-E/RT) = scale * poly
+    const double sc = scale * ca, hs = p.c_heat * sc;
+    dx[0] = fma(-sc, poly, fma(-p.thru, ca, a.feed_c));                           // :53
+    dx[1] = fma(hs, poly, fma(p.c_T, T, a.heat0));                                // :54-58
   }
 };
 

@@ -212,7 +212,7 @@ fast_rollout_kernel(const __grid_constant__ pcg_desc d, const __grid_constant__ 
 #pragma unroll
       for (int i = 0; i < NX; i += 2) {
         double za[EPT], zb[EPT];
-        draw_state_pair<EPT, NOISE == PCG_NOISE_PHILOX_F32>(gid0, static_cast<uint32_t>(cur.t_new), i / 2, key, za, zb);
+        draw_state_pair<EPT, NOISE == PCG_NOISE_PHILOX_F32>(gid0, static_cast<uint32_t>(cur.t_new), i / 2, key, kIcdfTab, za, zb);
 #pragma unroll
         for (int e = 0; e < EPT; ++e) {
           cur.z[e][i] = za[e];

@@ -513,8 +513,8 @@ rollout_kernel(const __grid_constant__ pcg_desc d, const __grid_constant__ pcg_i
 #pragma unroll
         for (int i = 0; i < NX; i += 2) {
           double za[EPT], zb[EPT];
-          if (noise == PCG_NOISE_PHILOX) draw_state_pair<EPT, false>(gid0, static_cast<uint32_t>(t_new), i / 2, key, za, zb);
-          else draw_state_pair<EPT, true>(gid0, static_cast<uint32_t>(t_new), i / 2, key, za, zb);
+          if (noise == PCG_NOISE_PHILOX) draw_state_pair<EPT, false>(gid0, static_cast<uint32_t>(t_new), i / 2, key, kIcdfTab, za, zb);
+          else draw_state_pair<EPT, true>(gid0, static_cast<uint32_t>(t_new), i / 2, key, kIcdfTab, za, zb);
 #pragma unroll
           for (int e = 0; e < EPT; ++e) {
             z[e][i] = za[e];

@@ -41,6 +41,23 @@ PCG_DEV void mbar_wait(uint64_t* b, uint32_t parity) {   // acquire.cta; try_wai
   } while (!ok);
 }
 
+// models whose integrator-warp RHS reads the shared-memory 2^(j/256) table (exp_tab_split): M::EXP_TAB
+template <class M, class = void>
+struct uses_exp_tab : std::false_type {};
+template <class M>
+struct uses_exp_tab<M, std::enable_if_t<M::EXP_TAB>> : std::true_type {};
+
+template <class M>
+PCG_DEV void fill_exp_tab(double* tab) {          // whole CTA, before the __syncthreads that publishes the barriers
+  if constexpr (uses_exp_tab<M>::value) {
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) tab[i] = kExp2Tab[i];
+  }
+}
+template <class M>
+PCG_DEV void bind_exp_tab(typename M::Aux& a, const double* tab) {
+  if constexpr (uses_exp_tab<M>::value) a.tab = tab;
+}
+
 template <class M, int RING = kWsRing>
 struct WsPair {
   double2 a[RING][M::NU][32];
@@ -56,6 +73,8 @@ ws_rollout_kernel(const __grid_constant__ pcg_desc d, const __grid_constant__ pc
                   const __grid_constant__ Derived<M, TB> dv, const int64_t n, const int t0, const int k_steps) {
   constexpr int NX = M::NX, NU = M::NU, ND = M::ND, NUK = NU + ND, EPT = 2, R = kWsRing;
   __shared__ __align__(16) WsPair<M> sm[W];
+  __shared__ double exp_tab[uses_exp_tab<M>::value ? 256 : 1];
+  fill_exp_tab<M>(exp_tab);
   // Role placement.  A warp's scheduler (SM sub-partition) is its hardware slot %warpid mod 4 and the CTAs of an
   // SM occupy consecutive slots, so a fixed (integrator, finisher) order would put every integrator warp -- the
   // FP64-heavy role -- on the same two sub-partitions.  Warp 2p / 2p+1 form pair p; which of the two integrates
@@ -121,7 +140,10 @@ ws_rollout_kernel(const __grid_constant__ pcg_desc d, const __grid_constant__ pc
       to_uk(a_raw, uk);
       typename M::Aux aux[EPT];
 #pragma unroll
-      for (int e = 0; e < EPT; ++e) M::prep(dv.p, uk[e], aux[e]);
+      for (int e = 0; e < EPT; ++e) {
+        M::prep(dv.p, uk[e], aux[e]);
+        bind_exp_tab<M>(aux[e], exp_tab);
+      }
       rk_step_fixed<M, TB, EPT>(dv, aux, x, uk);                               // integrator.py:90-107
 #pragma unroll
       for (int i = 0; i < NX; ++i) sp.x[s][i][lane] = make_double2(x[0][i], x[1][i]);
@@ -280,7 +302,7 @@ ws_rollout_kernel(const __grid_constant__ pcg_desc d, const __grid_constant__ pc
 #pragma unroll
       for (int i = 0; i < NX; i += 2) {
         double za[EPT], zb[EPT];
-        draw_state_pair<EPT, NOISE == PCG_NOISE_PHILOX_F32>(gid0, static_cast<uint32_t>(t_new), i / 2, key, za, zb);
+        draw_state_pair<EPT, NOISE == PCG_NOISE_PHILOX_F32>(gid0, static_cast<uint32_t>(t_new), i / 2, key, kIcdfTab, za, zb);
 #pragma unroll
         for (int e = 0; e < EPT; ++e) {
           z[e][i] = za[e];

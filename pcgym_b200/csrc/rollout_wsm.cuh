@@ -27,23 +27,32 @@ constexpr int kWsmMaxTiles = 8;    // integrator warps per CTA (<= 512 envs per 
 constexpr int kWsmRing = 16;
 static_assert(kWsmRing >= kWsmWarps - 2 && (kWsmRing & (kWsmRing - 1)) == 0, "ring depth vs finisher count");
 
-template <class M>
+constexpr int kWsmSpMax = 256;     // staged setpoint schedule: k_steps + 1 <= kWsmSpMax time indices per setpoint
+
+// NOISE / SPS decide which tables the CTA stages: the inverse-normal-CDF coefficients (16 KB) only when the finishers
+// draw in fp64, the setpoint schedule only when it is shared by all envs (the reference's form: io.sp_se == 0)
+template <class M, int NOISE, int NSP, bool SPS>
 struct WsmShared {
   WsPair<M, kWsmRing> tile[kWsmMaxTiles];
   uchar2 done0[kWsmMaxTiles][32];   // sticky done flag each env entered the launch with
   int next_task;
+  double exp_tab[uses_exp_tab<M>::value ? 256 : 1];   // 2^(j/256) for exp_tab_split (integrator warps)
+  double icdf[NOISE == PCG_NOISE_PHILOX ? 256 * 8 : 2];   // kIcdfTab (finishers)
+  double sp[SPS ? NSP : 1][SPS ? kWsmSpMax : 1];      // SP[j][t0 + i], i = 0..k_steps
 };
 
-// NSP = number of setpoints (1 or 2), CONU = some constraint reads an input: compile-time, so the finisher carries
-// no dead reward / setpoint / input-column work and no branch for it
-template <class M, class TB, int NOISE, int NSP, bool CONU>
+// NSP = number of setpoints (1 or 2), CONU = some constraint reads an input, SPS = the setpoint schedule is shared by
+// all envs and short enough to be staged in shared memory: compile-time, so the finisher carries no dead reward /
+// setpoint / input-column work and no branch for it
+template <class M, class TB, int NOISE, int NSP, bool CONU, bool SPS>
 __global__ void __launch_bounds__(32 * kWsmWarps, 1)
 wsm_rollout_kernel(const __grid_constant__ pcg_desc d, const __grid_constant__ pcg_io io,
                    const __grid_constant__ Derived<M, TB> dv, const int64_t n, const int t0, const int k_steps,
                    const int64_t envs_per_cta, const int n_tiles) {
   constexpr int NX = M::NX, NU = M::NU, ND = M::ND, NUK = NU + ND, EPT = 2, R = kWsmRing;
   extern __shared__ __align__(16) unsigned char wsm_raw[];
-  WsmShared<M>& sh = *reinterpret_cast<WsmShared<M>*>(wsm_raw);
+  using Shared = WsmShared<M, NOISE, NSP, SPS>;
+  Shared& sh = *reinterpret_cast<Shared*>(wsm_raw);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t cta_base = static_cast<int64_t>(blockIdx.x) * envs_per_cta;
   const int64_t cta_end = (cta_base + envs_per_cta < n) ? cta_base + envs_per_cta : n;
@@ -63,6 +72,16 @@ wsm_rollout_kernel(const __grid_constant__ pcg_desc d, const __grid_constant__ p
     }
   }
   if (threadIdx.x == 0) sh.next_task = 0;
+  fill_exp_tab<M>(sh.exp_tab);
+  if constexpr (NOISE == PCG_NOISE_PHILOX) {
+    for (int i = threadIdx.x; i < 256 * 8; i += blockDim.x) sh.icdf[i] = kIcdfTab[i];
+  }
+  if constexpr (SPS) {               // SP[j][t0 .. t0 + k_steps] (t0 + k_steps <= N - 1: abi.cu validates)
+    for (int i = threadIdx.x; i < NSP * (k_steps + 1); i += blockDim.x) {
+      const int j = i / (k_steps + 1), c = i - j * (k_steps + 1);
+      sh.sp[j][c] = io.sp[j * io.sp_sj + static_cast<int64_t>(t0 + c) * io.sp_st];
+    }
+  }
   __syncthreads();
 
   auto to_uk = [&](const double (&a_raw)[NU][EPT], double (&uk)[EPT][NUK]) {   // pcgym.py:372-375, 386-414
@@ -105,7 +124,10 @@ wsm_rollout_kernel(const __grid_constant__ pcg_desc d, const __grid_constant__ p
       to_uk(a_raw, uk);
       typename M::Aux aux[EPT];
 #pragma unroll
-      for (int e = 0; e < EPT; ++e) M::prep(dv.p, uk[e], aux[e]);
+      for (int e = 0; e < EPT; ++e) {
+        M::prep(dv.p, uk[e], aux[e]);
+        bind_exp_tab<M>(aux[e], sh.exp_tab);
+      }
       rk_step_fixed<M, TB, EPT>(dv, aux, x, uk);                               // integrator.py:90-107
 #pragma unroll
       for (int i = 0; i < NX; ++i) sp.x[s][i][lane] = make_double2(x[0][i], x[1][i]);
@@ -232,14 +254,26 @@ wsm_rollout_kernel(const __grid_constant__ pcg_desc d, const __grid_constant__ p
 
     // SP[t] (shown in the observation) and SP[t+1] (enters the reward)
     double spc[NSP][EPT], spn[NSP][EPT];
-    const uint32_t sp_st = static_cast<uint32_t>(io.sp_st), sp_se = static_cast<uint32_t>(io.sp_se);
+    if constexpr (SPS) {                                    // one value for the whole warp, from shared memory
 #pragma unroll
-    for (int j = 0; j < NSP; ++j) {
-      const uint32_t si = j * static_cast<uint32_t>(io.sp_sj) + env0 * sp_se + static_cast<uint32_t>(t) * sp_st;
+      for (int j = 0; j < NSP; ++j) {
+        const double c = sh.sp[j][k], nx = sh.sp[j][k + 1];
 #pragma unroll
-      for (int e = 0; e < EPT; ++e) {
-        spc[j][e] = io.sp[si + e * sp_se];
-        spn[j][e] = io.sp[si + e * sp_se + sp_st];
+        for (int e = 0; e < EPT; ++e) {
+          spc[j][e] = c;
+          spn[j][e] = nx;
+        }
+      }
+    } else {
+      const uint32_t sp_st = static_cast<uint32_t>(io.sp_st), sp_se = static_cast<uint32_t>(io.sp_se);
+#pragma unroll
+      for (int j = 0; j < NSP; ++j) {
+        const uint32_t si = j * static_cast<uint32_t>(io.sp_sj) + env0 * sp_se + static_cast<uint32_t>(t) * sp_st;
+#pragma unroll
+        for (int e = 0; e < EPT; ++e) {
+          spc[j][e] = io.sp[si + e * sp_se];
+          spn[j][e] = io.sp[si + e * sp_se + sp_st];
+        }
       }
     }
 
@@ -254,7 +288,7 @@ wsm_rollout_kernel(const __grid_constant__ pcg_desc d, const __grid_constant__ p
 #pragma unroll
       for (int i = 0; i < NX; i += 2) {
         double za[EPT], zb[EPT];
-        draw_state_pair<EPT, NOISE == PCG_NOISE_PHILOX_F32>(gid0, static_cast<uint32_t>(t_new), i / 2, key, za, zb);
+        draw_state_pair<EPT, NOISE == PCG_NOISE_PHILOX_F32>(gid0, static_cast<uint32_t>(t_new), i / 2, key, sh.icdf, za, zb);
 #pragma unroll
         for (int e = 0; e < EPT; ++e) {
           z[e][i] = za[e];

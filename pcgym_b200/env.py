@@ -233,8 +233,19 @@ class make_env:
 
         self._host_tables()
         self._desc = self._build_desc()
+        # step() returns info["obs"] BEFORE the partial-observation mask (pcgym.py:489-498), so its launches run with
+        # the mask off and the mask is applied afterwards; rollout() applies it in the kernel
+        self._desc_step = self._desc
+        if self._desc.obs_zero_mask:
+            self._desc_step = nat.Desc.from_buffer_copy(self._desc)
+            self._desc_step.obs_zero_mask = 0
         self._dev_ready = False
         self.t = 0
+        # Episode counter: the reference draws fresh np.random values every step and every reset (pcgym.py:257-260,
+        # 458, 464).  Here the noise is a pure function of (key, env, t), so the key advances with the episode:
+        # key = seed + episode * 0x9E3779B97F4A7C15 (mod 2^64); reset() / rewind() start the next episode,
+        # reset(episode=k) / rewind(episode=k) pin it (reproducible runs, CUDA-graph capture).
+        self.episode = -1
 
     # ------------------------------------------------------------------ constraints: callable -> affine form
     def _affine_constraints(self):
@@ -416,6 +427,7 @@ class make_env:
                 if names[i] not in self.partial_observation:
                     mask |= 1 << i
         self._obs_mask_bits = mask
+        self._mask_rows = [i for i in range(nx) if mask >> i & 1]
         d.obs_zero_mask = 0 if self._host_reward else mask
 
         d.noise = nat.NOISE["off"]
@@ -559,14 +571,21 @@ class make_env:
         return io
 
     # ------------------------------------------------------------------ reset (pcgym.py:263-349)
+    def _begin_episode(self, episode=None):
+        self.episode = int(episode) if episode is not None else self.episode + 1
+        key = (self.seed + self.episode * 0x9E3779B97F4A7C15) & (2 ** 64 - 1)
+        self._desc.seed = key
+        self._desc_step.seed = key
+
     def reset(self, seed: int = 0, **kwargs):
         self._ensure_device()
         self._join_pipe()
         self.t = 0
+        self._begin_episode(kwargs.get("episode"))
         nx, n = self.Nx_oracle, self.n_envs
         x0 = self._x0_dev.clone()
         gen = torch.Generator(device=self.device)
-        gen.manual_seed((self.seed * 1000003 + int(seed) + self.env_id0) & (2 ** 63 - 1))
+        gen.manual_seed((self.seed * 1000003 + int(seed) + self.env_id0 + 7919 * self.episode) & (2 ** 63 - 1))
         if self.uncertainty_percentages is not None and "x0" in self.uncertainty_percentages:
             for idx, unc in enumerate(self.uncertainty_percentages["x0"]):         # iterates keys, as :286-288
                 x0[idx] = self._perturb(x0[idx], float(unc), gen)
@@ -653,14 +672,20 @@ class make_env:
             z = z.to(device=self.device, dtype=torch.float64).reshape(n, self.Nx_oracle).T.contiguous()[None]
         a_save_old = self._a_save.clone() if (self._host_reward and self.a_delta) else None
         t_old = self.t
-        out = self._launch(self._a_step, 1, want_x=False, z=z)
+        out = self._launch(self._a_step, 1, want_x=False, z=z, desc=self._desc_step)
         obs_soa, r, done, violated = out["obs"][0], out["reward"][0], out["done"][0], out["violated"][0]
         if self._copy_outputs or self._host_reward:
             obs_soa, r = obs_soa.clone(), r.clone()
         if self._host_reward:
             r, obs_soa = self._custom_reward(obs_soa, self._a_step[0], a_save_old, t_old, violated.view(torch.bool), numpy_in)
+        elif self._obs_mask_bits:
+            # info["obs"] keeps the unmasked normalised observation (pcgym.py:489), the returned one is masked (:495-498)
+            self.info["obs"] = obs_soa.T.clone()
+            obs_soa = obs_soa.clone() if not self._copy_outputs else obs_soa
+            obs_soa[self._mask_rows] = 0
         self._last_obs = obs_soa
-        self.info["obs"] = obs_soa.T
+        if not self._obs_mask_bits or self._host_reward:
+            self.info["obs"] = obs_soa.T
         self.info["violated"] = violated.view(torch.bool).clone() if self._copy_outputs else violated.view(torch.bool)
         self.info["status"] = self._status
         if n == 1 and numpy_in:
@@ -827,8 +852,8 @@ class make_env:
             main.synchronize()
         self._pipe_prev = None
 
-    def _launch(self, a, K, want_x, z=None, bufs=None):
-        d = self._desc
+    def _launch(self, a, K, want_x, z=None, bufs=None, desc=None):
+        d = self._desc if desc is None else desc
         if d.noise == nat.NOISE["external"] and z is None:
             raise ValueError("noise_mode='external' needs the standard normals `z`")
         if bufs is None:
@@ -839,15 +864,17 @@ class make_env:
             nat.check(nat.lib().pcg_rollout(ctypes.byref(d), ctypes.byref(io), self.n_envs, self.t, K,
                                             ctypes.c_void_p(stream)))
         self.t += K
-        if d.ocp_mode == 2:
-            d.ocp_mode = 1                   # io.u_prev is valid from now on (it survives reset(), as `self.u_prev` does)
+        if d.ocp_mode == 2:                  # io.u_prev is valid from now on (it survives reset(), as `self.u_prev` does)
+            self._desc.ocp_mode = self._desc_step.ocp_mode = 1
         return bufs
 
-    def rewind(self, t: int = 0):
+    def rewind(self, t: int = 0, episode=None):
         """Begin a new episode from the CURRENT device state: only the time index and the sticky done flag
-        are cleared (no x0 copy, no allocation).  Continuing-task rollouts and the benchmark use this."""
+        are cleared (no x0 copy, no allocation) and the noise key moves on to the next episode (or to `episode`).
+        Continuing-task rollouts and the benchmark use this."""
         if not self._dev_ready:
             raise RuntimeError("call reset() before rewind()")
+        self._begin_episode(episode)
         self.t = int(t)
         self._done_state.zero_()
         self.done = False

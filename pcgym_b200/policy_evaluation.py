@@ -146,7 +146,9 @@ class policy_eval:
                 self._episode(policy, o_static, tuple(b.clone() for b in bufs))
             torch.cuda.current_stream(env.device).wait_stream(s)
             torch.cuda.synchronize(env.device)
-            env.reset()
+            # same episode index as the warm-up: the noise key is a by-value kernel argument, so the captured episode
+            # replays THIS episode's measurement noise every time (a fresh key needs a fresh capture)
+            env.reset(episode=env.episode)
             static_bufs = tuple(b.clone() for b in bufs)
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):

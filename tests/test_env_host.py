@@ -254,22 +254,41 @@ def test_affine_probe_recovers_the_matrices_and_rejects_oversize():
         models.AffineCustomModel(Big())
 
 
-def test_log_table_is_reproducible():
-    """pcgym_b200/csrc/logtab.inc is exactly what tools/gen_logtab.py writes (60-digit decimal arithmetic)."""
+def test_math_tables_are_reproducible():
+    """csrc/exp2tab.inc (2^(j/256), 60-digit decimal arithmetic) and csrc/icdftab.inc (inverse normal CDF segments) are
+    exactly what their generators under tools/ write; spot values are checked against their definitions."""
     import os
     import subprocess
     import sys
     import tempfile
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    want = open(os.path.join(root, "pcgym_b200", "csrc", "logtab.inc")).read()
-    src = open(os.path.join(root, "tools", "gen_logtab.py")).read()
-    with tempfile.TemporaryDirectory() as tmp:
-        os.makedirs(os.path.join(tmp, "tools")); os.makedirs(os.path.join(tmp, "pcgym_b200", "csrc"))
-        open(os.path.join(tmp, "tools", "gen_logtab.py"), "w").write(src)
-        subprocess.run([sys.executable, os.path.join(tmp, "tools", "gen_logtab.py")], check=True, capture_output=True)
-        got = open(os.path.join(tmp, "pcgym_b200", "csrc", "logtab.inc")).read()
-    assert got == want
-    rows = [ln for ln in want.splitlines() if ln.startswith("{")]
-    assert len(rows) == 128
-    inv0, m2ln0 = (float.fromhex(v.strip(" {},")) for v in rows[0].split("//")[0].rstrip(",").strip("{}").split(","))
-    assert abs(inv0 - 1 / (1 + 0.5 / 128)) < 1e-16 and abs(m2ln0 + 2 * np.log(1 / inv0)) < 1e-16
+    for gen, inc in (("gen_exp2tab.py", "exp2tab.inc"), ("gen_icdf_tab.py", "icdftab.inc")):
+        want = open(os.path.join(root, "pcgym_b200", "csrc", inc)).read()
+        src = open(os.path.join(root, "tools", gen)).read()
+        with tempfile.TemporaryDirectory() as tmp:
+            os.makedirs(os.path.join(tmp, "tools")); os.makedirs(os.path.join(tmp, "pcgym_b200", "csrc"))
+            open(os.path.join(tmp, "tools", gen), "w").write(src)
+            subprocess.run([sys.executable, os.path.join(tmp, "tools", gen)], check=True, capture_output=True)
+            got = open(os.path.join(tmp, "pcgym_b200", "csrc", inc)).read()
+        assert got == want, inc
+    vals = [float(v) for ln in open(os.path.join(root, "pcgym_b200", "csrc", "exp2tab.inc")) if not ln.startswith("//")
+            for v in ln.strip().rstrip(",").split(",")]
+    assert len(vals) == 256 and vals[0] == 1.0 and abs(vals[128] - 2 ** 0.5) < 3e-16 and abs(vals[255] - 2 ** (255 / 256)) < 3e-16
+
+
+def test_noise_transform_host_model_matches_the_inverse_normal_cdf():
+    """tests/noise_model.icdf_table_eval restates the device algorithm on the committed table: within 1e-13 of
+    scipy's ndtri over edge words, both tails and 2^21 random words; the Philox model passes the Random123 vectors."""
+    import noise_model as nm
+    rng = np.random.default_rng(1)
+    edge = np.array([0, 1, 2, 3, 7, 8, 15, 16, 0x7fffffff, 0x80000000, 0x80000001, 0xffffffff, 0xfffffffe, 0x3fffffff,
+                     0x40000000, 0x1fffffff, 0x20000000, 0x6a09e667, 0xb504f333], dtype=np.uint64)
+    w = np.concatenate([edge, rng.integers(0, 2 ** 32, 1 << 21, dtype=np.uint64), rng.integers(0, 4096, 4096, dtype=np.uint64),
+                        np.uint64(2 ** 32 - 1) - rng.integers(0, 4096, 4096, dtype=np.uint64)])
+    z, ref = nm.icdf_table_eval(w), nm.normal_from_word(w)
+    assert np.max(np.abs(z - ref)) < 1e-13
+    assert np.all(np.diff(nm.icdf_table_eval(np.sort(w))) >= 0)                 # monotone across every segment boundary
+    assert abs(ref[:2].min() + 6.33795775) < 1e-7 and abs(ref[11] - 6.33795775) < 1e-7
+    assert [int(v) for v in nm.philox4x32_10(0, 0, 0, 0, 0)] == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
+    assert [int(v) for v in nm.philox4x32_10(0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344, 0x299f31d0a4093822)] == \
+        [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]

@@ -101,16 +101,16 @@ def test_rollout_host_pipelined_equals_rollout_bitwise(chunks):
         assert out[k].device.type == "cpu" and out[k].is_pinned()
         assert same(out[k].to(torch.float64), ref[k].cpu().to(torch.float64)), k
     assert e2.t == K and torch.equal(e1.info["cons_info"], e2.info["cons_info"])
-    e2.reset()
+    e2.reset(episode=0)
     out2 = e2.rollout_host(acts, out=out, chunks=chunks, want_x=True)
     assert out2 is out and same(out["obs"], ref["obs"].cpu())
     with pytest.raises(ValueError):
         e2.rollout_host(acts.cuda())
     # back-to-back calls without waiting: two result sets alternate, host_sync() completes both
     a2 = torch.as_tensor(rng.uniform(-1, 1, (K, 1, n))).pin_memory()
-    e1.reset(); ref1 = {k: v.clone() for k, v in e1.rollout(acts.cuda()).items() if v is not None}
+    e1.reset(episode=3); ref1 = {k: v.clone() for k, v in e1.rollout(acts.cuda()).items() if v is not None}
     e1.rewind(); ref2 = e1.rollout(a2.cuda())
-    e2.reset()
+    e2.reset(episode=3)
     o1 = e2.rollout_host(acts.pin_memory(), chunks=chunks, wait=False)
     e2.rewind()
     o2 = e2.rollout_host(a2, chunks=chunks, wait=False)
@@ -307,54 +307,161 @@ def test_batch_rollout_vs_oracle(model, n_sub_oracle, integ, tol):
     assert out["done"][-1].all() and not out["done"][:-1].any()
 
 
-def test_headline_config_full_size_rtol_1e6():
-    """BASELINE config 3 at full size: 65 536 CSTR envs x 99 steps with the integrator bench.py times
-    (Tsit5, one step per control interval) against a converged oracle: north-star rtol 1e-6."""
+def _oracle_fixed(model, params, x0, acts, scheme="tsit5", n_sub=1):
+    """Noise-free trajectory [K, nx, n] by the oracle's own fixed-step scheme (same tableau, numpy arithmetic)."""
+    lo, hi = np.asarray(params["a_space"]["low"], float), np.asarray(params["a_space"]["high"], float)
+    dt = params["tsim"] / params["N"]
+    x = x0.T.copy()
+    xs = []
+    for k in range(acts.shape[0]):
+        u = (acts[k] + 1) * ((hi - lo) / 2)[:, None] + lo[:, None]
+        x = oint.advance_fixed(model, x, u, dt, scheme=scheme, n_sub=n_sub)
+        xs.append(x.copy())
+    return np.stack(xs)
+
+
+class forced_kernel:
+    """pcg_set_kernel for the duration of a with-block (the request is per thread and sticky)."""
+    def __init__(self, name):
+        from pcgym_b200 import _native as nat
+        self.nat, self.name = nat, name
+
+    def __enter__(self):
+        self.prev = self.nat.lib().pcg_set_kernel(self.nat.KERNELS[self.name])
+        return self
+
+    def __exit__(self, *a):
+        self.nat.lib().pcg_set_kernel(self.prev)
+
+    def last(self):
+        return self.nat.lib().pcg_last_kernel().decode()
+
+
+# BASELINE batch sizes (SURVEY 8d): first_order 65 536, cstr 65 536, extraction 32 768; the others a quarter of that.
+# dt is the model's documented control interval except for multistage_extraction, whose explicit single step is only
+# stable for |lambda| dt < 3 (the documented dt = 1 needs the adaptive / Rosenbrock paths): dt = 0.004 here.
+MATRIX = [
+    ("cstr", 65536, "wsm", "wsm_rollout_kernel"),
+    ("cstr", 65536, "ws", "ws_rollout_kernel"),
+    ("cstr", 65536, "fast", "fast_rollout_kernel (software-pipelined, 2 envs/thread)"),
+    ("cstr", 65536, "fast_ept1", "fast_rollout_kernel (software-pipelined, 1 env/thread)"),
+    ("cstr", 65536, "generic", "rollout_kernel (generic, 2 envs/thread)"),
+    ("cstr", 65535, "auto", "fast_rollout_kernel (software-pipelined, 1 env/thread)"),       # odd batch: 64-bit rows
+    ("cstr", 20000, "auto", "wsm_rollout_kernel"),                                           # partial last CTA
+    ("first_order_system", 65536, "fast", "fast_rollout_kernel (software-pipelined, 2 envs/thread)"),
+    ("first_order_system", 65536, "fast_ept1", "fast_rollout_kernel (software-pipelined, 1 env/thread)"),
+    ("first_order_system", 65536, "generic", "rollout_kernel (generic, 2 envs/thread)"),
+    ("multistage_extraction", 32768, "fast", "fast_rollout_kernel (software-pipelined, 1 env/thread)"),
+    ("multistage_extraction", 32768, "generic", "rollout_kernel (generic, 1 env/thread)"),
+    ("four_tank", 16384, "fast", "fast_rollout_kernel (software-pipelined, 1 env/thread)"),
+    ("four_tank", 16384, "generic", "rollout_kernel (generic, 1 env/thread)"),
+    ("crystallization", 16384, "fast", "fast_rollout_kernel (software-pipelined, 1 env/thread)"),
+    ("crystallization", 16384, "generic", "rollout_kernel (generic, 1 env/thread)"),
+    ("biofilm_reactor", 8192, "fast", "fast_rollout_kernel (software-pipelined, 1 env/thread)"),
+    ("biofilm_reactor", 8192, "generic", "rollout_kernel (generic, 1 env/thread)"),
+]
+
+
+@pytest.mark.parametrize("model,n,request_,kernel", MATRIX)
+def test_every_straight_line_kernel_against_the_oracle_same_scheme(model, n, request_, kernel):
+    """Every kernel family x every north-star model at the BASELINE batch sizes, one Tsit5 step per control interval
+    (the scheme the straight-line kernels are built for), two constraints on state 0, SP reward with penalty:
+    x against the oracle's own Tsit5 step (same tableau, numpy arithmetic: 1e-11), reward / observation / flags
+    against the reference formulae evaluated on the oracle's x.  pcg_last_kernel() proves which kernel ran."""
+    K = 12
+    params, x0, acts, key, sp = batch_setup(model, n, K)
+    if model == "multistage_extraction":
+        params["tsim"] = params["N"] * 0.004
+    x00 = BATCH[model]["x0"][0]
+    c_lo, c_hi = 0.97 * x00, 1.03 * x00
+    params.update(constraints=lambda x, u: np.array([c_lo - x[0], x[0] - c_hi]), done_on_cons_vio=False, r_penalty=True,
+                  constraint_units="physical", integrator=HEADLINE)
+    with forced_kernel(request_) as fk:
+        env = _env(params)
+        env.reset()
+        out = env.rollout(torch.as_tensor(acts))
+        torch.cuda.synchronize()
+        assert fk.last().startswith(kernel), fk.last()
+    xs = _oracle_fixed(model, params, x0, acts)
+    got_x = out["x"].cpu().numpy()
+    assert rel(got_x, xs) < 1e-11, (model, request_, rel(got_x, xs))
+    meta = orhs.MODELS[model]
+    si = meta["states"].index(key)
+    g = np.stack([c_lo - xs[:, 0], xs[:, 0] - c_hi], axis=1)                       # [K, 2, n]
+    viol = (g > 0).any(axis=1)
+    sure = (np.abs(g) > 1e-9 * x00).all(axis=1)                                     # a g within rounding of 0 may flip
+    got_v = out["violated"].cpu().numpy().astype(bool)
+    assert np.array_equal(got_v[sure], viol[sure]) and sure.mean() > 0.999 and viol.any() and not viol.all()
+    want_r = -((xs[:, si] - sp[1:K + 1, None]) ** 2) * 3.0 - 1000.0 * viol
+    np.testing.assert_allclose(out["reward"].cpu().numpy()[sure], want_r[sure], rtol=1e-9, atol=1e-9 * max(1.0, np.abs(want_r).max()))
+    np.testing.assert_allclose(env.info["cons_info"][:, 1:].permute(1, 0, 2).cpu().numpy(), g, rtol=0, atol=1e-10 * x00)
+    lo, hi = params["o_space"]["low"], params["o_space"]["high"]
+    want_obs = 2 * (np.concatenate([xs, np.broadcast_to(sp[:K, None, None], (K, 1, n))], axis=1) - lo[None, :, None]) / (hi - lo)[None, :, None] - 1
+    np.testing.assert_allclose(out["obs"].cpu().numpy(), want_obs, rtol=0, atol=1e-10)
+    assert int(env.status.max()) == 0
+    assert out["done"][-1].all() and not out["done"][:-1].any()
+
+
+def test_headline_config_full_size_noise_on():
+    """BASELINE config 3 EXACTLY as bench.py times it -- 65 536 CSTR envs x 99 intervals, Tsit5 x 1, Philox noise ON,
+    constraints + penalty, the per-SM warp-specialised kernel -- against the oracle:
+      * x: same scheme 1e-11, converged solution at the north-star rtol 1e-6;
+      * observation: the reference formula (pcgym.py:453-493) on the oracle's x with the documented draw
+        z = Phi^-1 of the Philox word (tests/noise_model.py, scipy ndtri);
+      * reward / violated / cons_info / done: the reference formulae on the oracle's x."""
     import bench
-    params, acts = bench.cstr_headline(n_envs=65536, device="cuda", seed=0)
-    params = dict(params, noise=False)
+    import noise_model as nm
+    from pcgym_b200 import _native as nat
+    n = 65536
+    params, acts = bench.cstr_headline(n_envs=n, device="cuda", seed=0)
     env = _env(params)
     env.reset()
     out = env.rollout(acts)
-    x0 = params["x0"][:, :2].cpu().numpy().T.copy()
+    torch.cuda.synchronize()
+    assert nat.lib().pcg_last_kernel().decode().startswith("wsm_rollout_kernel")
+    assert env._desc.noise == nat.NOISE["philox"]
+    x0 = params["x0"][:, :2].cpu().numpy()
     a = acts.cpu().numpy()
-    x = x0
+    K = a.shape[0]
+    p1 = {"a_space": params["a_space"], "tsim": params["tsim"], "N": params["N"]}
+    xs = _oracle_fixed("cstr", p1, x0, a)
+    got_x = out["x"].cpu().numpy()
+    assert rel(got_x, xs) < 1e-11, rel(got_x, xs)
+    x = x0.T.copy()
     worst = 0.0
-    for k in range(a.shape[0]):
-        u = (a[k] + 1) * 3.5 + 295.0
-        x = oint.advance_dense("cstr", x, u, 0.25, n_sub=16)
-        worst = max(worst, rel(out["x"][k].cpu().numpy(), x))
+    for k in range(K):
+        x = oint.advance_dense("cstr", x, (a[k] + 1) * 3.5 + 295.0, 0.25, n_sub=16)
+        worst = max(worst, rel(got_x[k], x))
     assert worst < 1e-6, worst
+    sp = np.array(params["SP"]["Ca"])
+    lo, hi = params["o_space"]["low"], params["o_space"]["high"]
+    gid = np.arange(n)
+    got_obs, got_r = out["obs"].cpu().numpy(), out["reward"].cpu().numpy()
+    got_v, got_g = out["violated"].cpu().numpy().astype(bool), env.info["cons_info"].cpu().numpy()
+    for k in range(K):
+        z = nm.normals(env._desc.seed, gid, k + 1, 2)
+        noisy = xs[k] * (1 + z * 0.001)                                              # pcgym.py:458
+        want = np.concatenate([noisy, np.full((1, n), sp[k])])                        # SP[t] in the observation
+        want = 2 * (want - lo[:, None]) / (hi - lo)[:, None] - 1
+        np.testing.assert_allclose(got_obs[k], want, rtol=0, atol=5e-10, err_msg=f"obs {k}")
+        g = np.stack([319 - xs[k, 1], xs[k, 1] - 331])
+        np.testing.assert_allclose(got_g[:, k + 1], g, rtol=0, atol=1e-8)
+        viol = (g > 0).any(axis=0)
+        sure = (np.abs(g) > 1e-7).all(axis=0)
+        assert np.array_equal(got_v[k][sure], viol[sure])
+        r = -((xs[k, 0] - sp[k + 1]) ** 2) * 1e3 - 1000.0 * viol                       # SP[t+1], noise-free state
+        np.testing.assert_allclose(got_r[k][sure], r[sure], rtol=1e-8, atol=1e-10)
+    assert out["done"][-1].all() and not out["done"][:-1].any()
     assert int(env.status.max()) == 0
-    # violated flag and penalty are consistent with the stored constraint values
-    g = env.info["cons_info"][:, 1:, :]
-    v = (g > 0).any(dim=0)
-    assert torch.equal(v, out["violated"].bool())
 
 
 # ----------------------------------------------------------------------------- noise
-def philox_py(ctr, key):
-    M0, M1, W0, W1 = 0xD2511F53, 0xCD9E8D57, 0x9E3779B9, 0xBB67AE85
-    c, k = list(ctr), list(key)
-    for _ in range(10):
-        p0, p1 = M0 * c[0], M1 * c[2]
-        c = [(p1 >> 32) ^ c[1] ^ k[0], p1 & 0xFFFFFFFF, (p0 >> 32) ^ c[3] ^ k[1], p0 & 0xFFFFFFFF]
-        k = [(k[0] + W0) & 0xFFFFFFFF, (k[1] + W1) & 0xFFFFFFFF]
-    return c
-
-
-def test_philox_known_answers_host_model():
-    # Random123 kat_vectors, philox4x32-10
-    assert philox_py([0, 0, 0, 0], [0, 0]) == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
-    assert philox_py([0xffffffff] * 4, [0xffffffff] * 2) == [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
-    assert philox_py([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], [0xa4093822, 0x299f31d0]) == \
-        [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]
-
-
 @pytest.mark.parametrize("n,id0", [(8, 1000), (7, 1001)])      # even batch: 2 envs/thread kernels; odd: 1 env/thread
-def test_device_noise_is_philox_boxmuller(n, id0):
+def test_device_noise_is_philox_inverse_cdf(n, id0):
     """z recovered from the kernel's noisy observation equals the documented draw (csrc/philox.cuh): Philox4x32-10
-    block of (env pair gid >> 1, t, state pair), words (2p, 2p+1) for env parity p, 32-bit uniforms, Box-Muller."""
+    block of (env pair gid >> 1, t, state pair), word 2 (gid & 1) + (state & 1), z = Phi^-1((w + 1/2) 2^-32) -- the
+    host model uses scipy's ndtri, not the kernel's table."""
+    import noise_model as nm
     params = cases.cstr_basic()
     seed = 0x1234567_89ABCDEF
     env = _env(params, n_envs=n, seed=seed, env_id0=id0, normalise_o=False, integrator=HEADLINE)
@@ -365,54 +472,44 @@ def test_device_noise_is_philox_boxmuller(n, id0):
     for k in range(3):
         x = out["x"][k].cpu().numpy()
         z = (out["obs"][k, :2].cpu().numpy() - x) / (x * pct)
-        for e in range(n):
-            gid = id0 + e
-            r = philox_py([(gid >> 1) & 0xFFFFFFFF, gid >> 33, k + 1, 0], [seed & 0xFFFFFFFF, seed >> 32])
-            w0, w1 = r[2 * (gid & 1)], r[2 * (gid & 1) + 1]
-            u0, u1 = (w0 + 0.5) * 2.0 ** -32, (w1 + 0.5) * 2.0 ** -32
-            rad = np.sqrt(-2 * np.log(u0))
-            np.testing.assert_allclose(z[:, e], [rad * np.cos(2 * np.pi * u1), rad * np.sin(2 * np.pi * u1)], rtol=0, atol=2e-9)
+        want = nm.normals(env._desc.seed, id0 + np.arange(n), k + 1, 2)
+        np.testing.assert_allclose(z, want, rtol=0, atol=2e-9)                # (obs - x) / (x pct) loses ~7 digits
 
 
 def test_normal_transform_accuracy_over_the_word_range():
-    """pcg_normal_pairs: the fp64 Box-Muller of csrc/philox.cuh (table log, Goldschmidt sqrt, integer quadrant
-    reduction) against numpy on edge words and 2^20 random ones; the fp32 evaluation to fp32 accuracy."""
+    """pcg_normal_pairs: the fp64 inverse-CDF draw of csrc/philox.cuh against scipy's ndtri on edge words, both
+    tails and 2^20 random words (1e-13); the fp32 Box-Muller evaluation to fp32 accuracy."""
+    import noise_model as nm
     from pcgym_b200 import _native as nat
     rng = np.random.default_rng(5)
-    edge = np.array([0, 1, 2, 0x1fffffff, 0x20000000, 0x20000001, 0x3fffffff, 0x40000000, 0x5fffffff, 0x60000000,
-                     0x7fffffff, 0x80000000, 0x9fffffff, 0xa0000000, 0xbfffffff, 0xc0000000, 0xdfffffff, 0xe0000000,
-                     0xfffffffe, 0xffffffff, 0x6a09e667, 0xb504f333, 0xb504f334], dtype=np.uint64)
-    w0 = np.concatenate([np.repeat(edge, len(edge)), rng.integers(0, 2 ** 32, 1 << 20, dtype=np.uint64)])
-    w1 = np.concatenate([np.tile(edge, len(edge)), rng.integers(0, 2 ** 32, 1 << 20, dtype=np.uint64)])
+    edge = np.array([0, 1, 2, 3, 7, 8, 0x1fffffff, 0x20000000, 0x20000001, 0x3fffffff, 0x40000000, 0x5fffffff, 0x60000000,
+                     0x7fffffff, 0x80000000, 0x80000001, 0x9fffffff, 0xa0000000, 0xbfffffff, 0xc0000000, 0xdfffffff,
+                     0xe0000000, 0xfffffffe, 0xffffffff, 0x6a09e667, 0xb504f333, 0xb504f334], dtype=np.uint64)
+    tails = np.concatenate([rng.integers(0, 1 << 14, 4096, dtype=np.uint64),
+                            np.uint64(2 ** 32 - 1) - rng.integers(0, 1 << 14, 4096, dtype=np.uint64)])
+    w0 = np.concatenate([np.repeat(edge, len(edge)), tails, rng.integers(0, 2 ** 32, 1 << 20, dtype=np.uint64)])
+    w1 = np.concatenate([np.tile(edge, len(edge)), tails[::-1], rng.integers(0, 2 ** 32, 1 << 20, dtype=np.uint64)])
     n = w0.size
     dw0 = torch.from_numpy(w0.astype(np.uint32).view(np.int32)).cuda()
     dw1 = torch.from_numpy(w1.astype(np.uint32).view(np.int32)).cuda()
-    u0 = (w0.astype(np.float64) + 0.5) * 2.0 ** -32
-    x = (w1.astype(np.float64) + 0.5) * 2.0 ** -31                # angle / pi in (0, 2)
-    q = np.rint(2 * x)
-    xr = x - q / 2                                                # exact reduction, as the kernel's integer one
-    sn, cs = np.sin(np.pi * xr), np.cos(np.pi * xr)
-    k = q.astype(np.int64) % 4
-    s_ref = np.choose(k, [sn, cs, -sn, -cs])
-    c_ref = np.choose(k, [cs, -sn, -cs, sn])
-    rad = np.sqrt(-2 * np.log(u0))
-    # fp32 evaluation: (k + 1/2) 2^-24 rounds to 1.0 for the top words, so the radius is only good to ~4e-4 there
-    for f32, tol in ((0, 1e-14), (1, 1e-3)):
+    for f32 in (0, 1):
         z0 = torch.empty(n, dtype=torch.float64, device="cuda")
         z1 = torch.empty_like(z0)
         nat.check(nat.lib().pcg_normal_pairs(dw0.data_ptr(), dw1.data_ptr(), z0.data_ptr(), z1.data_ptr(), n, f32,
                                              torch.cuda.current_stream().cuda_stream))
         torch.cuda.synchronize()
-        if f32:                                                   # 24-bit uniforms: compare on the truncated words
+        if f32:                                                   # 24-bit uniforms, Box-Muller of the word pair
             u0f = ((w0 >> np.uint64(8)).astype(np.float64) + 0.5) * 2.0 ** -24
             u1f = ((w1 >> np.uint64(8)).astype(np.float64) + 0.5) * 2.0 ** -24
             radf = np.sqrt(-2 * np.log(u0f))
             ref0, ref1 = radf * np.cos(2 * np.pi * u1f), radf * np.sin(2 * np.pi * u1f)
+            scale = np.maximum(1.0, radf)
+            assert np.max(np.abs(z0.cpu().numpy() - ref0) / scale) < 1e-3
+            assert np.max(np.abs(z1.cpu().numpy() - ref1) / scale) < 1e-3
         else:
-            ref0, ref1 = rad * c_ref, rad * s_ref
-        scale = np.maximum(1.0, rad)
-        assert np.max(np.abs(z0.cpu().numpy() - ref0) / scale) < tol
-        assert np.max(np.abs(z1.cpu().numpy() - ref1) / scale) < tol
+            assert np.max(np.abs(z0.cpu().numpy() - nm.normal_from_word(w0))) < 1e-13
+            assert np.max(np.abs(z1.cpu().numpy() - nm.normal_from_word(w1))) < 1e-13
+            np.testing.assert_allclose(z0.cpu().numpy(), nm.icdf_table_eval(w0), rtol=0, atol=5e-15)   # host restatement (no fma there)
 
 
 @pytest.mark.parametrize("mode", ["philox", "philox_f32"])

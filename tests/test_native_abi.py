@@ -80,6 +80,7 @@ def test_argument_validation_codes():
     assert call(d) == -6
     d = _valid_desc()
     assert call(d, n=0) == -6 and call(d, k=0) == -6 and call(d, t=-1) == -6
+    assert call(d, t=8, k=2) == -6 and call(d, t=0, k=10) == -6      # t0 + k_steps must stay within N - 1 = 9 intervals
     assert call(d) == -1                                   # x / a pointers missing
     io.x, io.a = 0x1004, 0x2000
     assert call(d) == -7                                   # misaligned
@@ -89,3 +90,11 @@ def test_argument_validation_codes():
     assert L.pcg_launch_count() == 0                       # nothing was launched by any of the above
     with pytest.raises(nat.NativeError):
         nat.check(-3)
+
+
+def test_kernel_request_knob():
+    L = nat.lib()
+    assert L.pcg_set_kernel(nat.KERNELS["wsm"]) == nat.KERNELS["auto"]          # returns the previous request
+    assert L.pcg_set_kernel(nat.KERNELS["auto"]) == nat.KERNELS["wsm"]
+    assert L.pcg_set_kernel(6) == -6 and L.pcg_set_kernel(-2) == -6
+    assert L.pcg_set_kernel(nat.KERNELS["auto"]) == nat.KERNELS["auto"]

@@ -55,3 +55,20 @@ def test_embedded_pairs(name):
     emb = b - E
     assert conditions(M, emb, 4) < 5e-14          # embedded 4th-order solution
     assert conditions(M, emb, 5) > 1e-5           # ... and genuinely not 5th
+
+
+@pytest.mark.parametrize("name,order", [("rk4", 4), ("dopri5", 5), ("tsit5", 5)])
+def test_oracle_tableaus_match_the_kernel_tableaus(name, order):
+    """oracle/integrate.py restates the coefficients from the literature; they satisfy the order conditions on
+    their own and equal what the kernels compile in."""
+    from oracle.integrate import TABLEAUS
+    tb = TABLEAUS[name]
+    S = len(tb["B"])
+    M = np.zeros((S, S))
+    for i, row in enumerate(tb["A"]):
+        M[i, : len(row)] = row
+    b = np.array(tb["B"])
+    assert conditions(M, b, order) < 5e-14
+    A, _ = parse({"rk4": "Rk4", "dopri5": "Dopri5", "tsit5": "Tsit5"}[name])
+    np.testing.assert_array_equal(A[:S, :S][np.tril_indices(S, -1)], M[np.tril_indices(S, -1)])
+    np.testing.assert_array_equal(A[S][:S], b)
