@@ -1,24 +1,36 @@
 #!/usr/bin/env python
 """Headline benchmark: env-steps/s for 65 536 batched CSTR envs per B200 (BASELINE.json config 3).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--config 2|3|4|5]
 
 One bench "step" = ONE pcg_rollout launch: all 65 536 envs of this GPU advanced through the 99 control
 intervals of an episode (N = 100), each interval = Tsit5 RK5(4) step of the CSTR ODE + Gaussian
 measurement noise + constraint flags + setpoint reward + observation normalisation (fp64).
 Weak scaling: every rank owns its own 65 536 envs (no collective on the step path).
 
+How the K steps are timed (round-2 change): the K launches (each preceded by the one-byte-per-env
+memset that starts a new episode) are captured ONCE in a CUDA graph and the timed region is one replay of that graph
+between two CUDA events, bracketed by barrier + synchronize.  The region is then limited by the device, not by how
+fast eight Python processes sharing one host can enqueue 3 ms of work (round 1's 8-GPU "cliff").  A second, eager
+pass times every launch with its own event pair: `roofline.kernel_ms` (max over ranks of the per-rank mean) and the
+per-rank table `per_rank` come from it, together with the host time one enqueue takes.
+
 Prints ONE JSON line (rank 0).  Keys beyond the driver contract:
   roofline      HBM roofline of the rollout kernel: algorithmic bytes / CUDA-event launch time
   cpu_baseline  the restated reference step() on the host cores (bounded sample)
-  e2e           same metric through make_env.rollout() with pinned HOST buffers, copies in the timed region
+  e2e           same metric through make_env.rollout_host() with pinned HOST buffers, copies in the timed region,
+                beside the pinned device->host copy ceiling measured at this rank count; `e2e.reduced` = the same call
+                bringing back only the episode return, the final observation and the done flag
+  per_rank      [graph ms per step, eager kernel ms, host enqueue us per launch] of every rank
   step_mode     the Gym-style one-interval-per-launch path (launch-latency bound), for information
 """
 from __future__ import annotations
 
 import argparse
+import glob
 import json
 import os
+import re
 import subprocess
 import sys
 import threading
@@ -40,7 +52,6 @@ K_STEPS = N_HORIZON - 1
 # SURVEY 8(d) quotes 82 B because it assumes per-env setpoint tensors (8 B more read per env-step); the
 # headline uses the reference's shared setpoint schedule, which costs no per-env traffic.
 BYTES_PER_ENV_STEP = 74
-NCU_DRAM_BYTES_PER_LAUNCH = 53310208 + 371888640      # profiles/r1_cstr_v8_wsm_ncu_summary.txt
 HEADLINE_INTEGRATOR = {"scheme": "tsit5", "adaptive": False, "n_sub": 1}
 
 
@@ -61,6 +72,9 @@ def cstr_headline(n_envs=N_ENVS, device="cuda", seed=0, env_id0=0):
         "noise": True, "noise_percentage": 0.001,
         "constraints": lambda x, u: np.array([319 - x[1], x[1] - 331]).reshape(-1,),
         "done_on_cons_vio": False, "r_penalty": True,
+        # g is evaluated on physical T in BOTH arms (oracle/baseline.py sets the same key): the reference's
+        # constraint_check un-normalises already-physical values when normalisation is on (pcgym.py:597-608), which
+        # would flag every env at every step; the default of make_env replicates that quirk, the headline opts out
         "constraint_units": "physical",
         "integrator": dict(HEADLINE_INTEGRATOR),
         "seed": seed, "env_id0": env_id0,
@@ -70,14 +84,18 @@ def cstr_headline(n_envs=N_ENVS, device="cuda", seed=0, env_id0=0):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    """nvidia-smi clocks / throttle reasons sampled every 100 ms while the GPU is under the benchmark's load
+    (B200_PROFILING.md).  Rank 0 only, started >= 2 s before the timed region (NVML initialisation enumerates every
+    GPU of the box and must not overlap a 3 ms measurement)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, gpu_index):
-        self.idx, self.rows, self.proc = gpu_index, [], None
+    def __init__(self, gpu_index, enabled=True):
+        self.idx, self.rows, self.proc, self.enabled = gpu_index, [], None, enabled
 
     def __enter__(self):
+        if not self.enabled:
+            return self
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-i", str(self.idx), "-lms", "100"], stdout=subprocess.PIPE, text=True)
@@ -89,7 +107,7 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
 
     def __exit__(self, *a):
         if self.proc:
@@ -99,17 +117,20 @@ class ClockSampler:
             except Exception:  # noqa: BLE001
                 self.proc.kill()
 
-    def summary(self):
-        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
-        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+    def summary(self, t_lo=None, t_hi=None):
+        rows = [r for t, r in self.rows if (t_lo is None or t >= t_lo) and (t_hi is None or t <= t_hi)] or [r for _, r in self.rows]
+        sm = [float(r[1]) for r in rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
         reasons = set()
-        for r in self.rows:
+        for r in rows:
             if len(r) >= 9:
                 for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
                     if v.lower().startswith("active"):
                         reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm),
+                "window": "100 ms samples while the captured K-step graph replays back to back: 1.5 s before, during and "
+                          "0.5 s after the timed replay"}
 
 
 def hbm_peak():
@@ -117,6 +138,20 @@ def hbm_peak():
     if os.path.exists(p):
         return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the headline kernel, from the newest committed ncu
+    summary of it under profiles/ (one `ncu --set full` capture per kernel change; never a live counter)."""
+    best = None
+    for f in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_cstr_*wsm*_ncu_summary.txt"))):
+        txt = open(f).read()
+        rd = re.search(r"DRAM read\s+([\d.]+)\s+(\w+)", txt)
+        wr = re.search(r"DRAM written\s+([\d.]+)\s+(\w+)", txt)
+        if rd and wr:
+            unit = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+            best = (int(float(rd.group(1)) * unit[rd.group(2)] + float(wr.group(1)) * unit[wr.group(2)]), os.path.relpath(f, ROOT))
+    return best or (None, None)
 
 
 # ------------------------------------------------------------------------------------------ reference arm
@@ -130,7 +165,7 @@ def run_reference(args):
     per = max(1, args.ref_envs_per_worker)
     for _ in range(max(args.warmup, 0) and 1):
         baseline.run(envs_per_worker=1, n_steps=20, cores=cores)
-    vals, total, busy = [], 0, 0.0
+    vals, total = [], 0
     t0 = time.perf_counter()
     for _ in range(args.steps):
         r = baseline.run(envs_per_worker=per, cores=cores)
@@ -160,19 +195,29 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", type=int, default=3, choices=[2, 3, 4, 5],
+                    help="BASELINE.json config: 3 = headline (default); 2 / 4 / 5 are run by tools/bench_models.py")
     ap.add_argument("--n-envs", type=int, default=N_ENVS, help="envs per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="time K eager launches instead of one graph replay")
+    ap.add_argument("--quick", action="store_true", help="A/B aid: kernel timing only, short JSON line (not a bench line)")
     ap.add_argument("--e2e-chunks", type=int, default=8, help="time slices pipelined by make_env.rollout_host")
     ap.add_argument("--ref-envs-per-worker", type=int, default=48)
     ap.add_argument("--noise-mode", default="philox", choices=["philox", "philox_f32", "off"],
-                    help="experiment knob; the headline is 'philox' (fp64 Box-Muller)")
+                    help="experiment knob; the headline is 'philox' (fp64 inverse-CDF draw)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    if args.config != 3:
+        sys.argv = [os.path.join(ROOT, "tools", "bench_models.py"), "--config", str(args.config), "--steps", str(args.steps),
+                    "--warmup", str(args.warmup)]
+        import runpy
+        return runpy.run_path(sys.argv[0], run_name="__main__")
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
 
     # CPU baseline first (rank 0, N=1 only), before this process touches CUDA: workers are spawned
     cpu = None
@@ -193,7 +238,7 @@ def main():
     numa_cpus = []
     if world > 1:
         sharding.init_from_env("nccl")
-        numa_cpus = sharding.bind_to_gpu_numa(local)       # pinned e2e buffers next to this rank's GPU
+        numa_cpus = sharding.bind_to_gpu_numa(local, local_world)   # disjoint CPU slice per rank, next to its GPU
     n = args.n_envs
     W, K = max(args.warmup, 3), args.steps
 
@@ -217,65 +262,135 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- resident-input throughput (`value`) + per-launch kernel time (roofline)
+    # ---- resident-input throughput (`value`): W eager warm-up steps, the K steps captured in one graph, >= 1.5 s of
+    # replays under the clock sampler, then ONE timed replay = exactly K steps
     for i in range(W):
         one_rollout(i)
     barrier()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
-    t_all0, t_all1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    l0 = lib.pcg_launch_count()
-    with ClockSampler(local) as clk:
-        barrier()
-        t_all0.record()
-        for i in range(K):
-            ev[i][0].record()
-            one_rollout(i)
-            ev[i][1].record()
-        t_all1.record()
-        barrier()
-        launches = lib.pcg_launch_count() - l0
-        kernel_name = "pcg::" + lib.pcg_last_kernel().decode() + " <cstr, tsit5, %s>" % args.noise_mode
-        # keep the GPU busy a little longer so the 100 ms sampler sees the loaded clocks
-        t_end = time.perf_counter() + 0.6
-        while time.perf_counter() < t_end:
+    kernel_name = "pcg::" + lib.pcg_last_kernel().decode() + " <cstr, tsit5, %s>" % args.noise_mode
+    graph = None
+    if not args.no_graph:
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
             one_rollout(0)
+        torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize()
-    total_ms = t_all0.elapsed_time(t_all1)
-    kern_ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
-    total_ms = sharding.max_over_ranks(total_ms, dev)
-    kern_ms_max = sharding.max_over_ranks(kern_ms, dev)
+        graph = torch.cuda.CUDAGraph()
+        l0 = lib.pcg_launch_count()
+        with torch.cuda.graph(graph):
+            for i in range(K):
+                one_rollout(i)
+        launches = lib.pcg_launch_count() - l0
+        env.t = K_STEPS
+
+    def timed_region():
+        if graph is not None:
+            graph.replay()
+        else:
+            for i in range(K):
+                one_rollout(i)
+
+    t_a, t_b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local, enabled=(rank == 0)) as clk:
+        t_end = time.perf_counter() + 1.5
+        while time.perf_counter() < t_end:
+            timed_region()
+        barrier()
+        c_lo = time.perf_counter() - 1.0
+        if graph is None:
+            l0 = lib.pcg_launch_count()
+        t_a.record()
+        timed_region()
+        t_b.record()
+        barrier()
+        if graph is None:
+            launches = lib.pcg_launch_count() - l0
+        t_end = time.perf_counter() + 0.5
+        while time.perf_counter() < t_end:
+            timed_region()
+        torch.cuda.synchronize()
+        c_hi = time.perf_counter()
+    total_ms_local = t_a.elapsed_time(t_b)
+    total_ms = sharding.max_over_ranks(total_ms_local, dev)
     env_steps_per_launch = n * K_STEPS
     value = world * env_steps_per_launch * K / (total_ms * 1e-3)
 
+    # ---- per-launch kernel time (roofline) and host enqueue cost: eager pass, one event pair per launch
+    barrier()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    enq = 0.0
+    for i in range(K):
+        env.rewind()
+        ev[i][0].record()
+        h0 = time.perf_counter()
+        env.rollout(ring[i % len(ring)])
+        enq += time.perf_counter() - h0
+        ev[i][1].record()
+    barrier()
+    kern_ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
+    kern_ms_max = sharding.max_over_ranks(kern_ms, dev)
+    per_rank = sharding.gather_over_ranks([total_ms_local / K, kern_ms, 1e6 * enq / K], dev)
+
+    if args.quick:
+        if rank == 0:
+            peak, _ = hbm_peak()
+            print(json.dumps({"quick": True, "kernel_ms": kern_ms_max, "graph_ms_per_step": total_ms / K,
+                              "frac": BYTES_PER_ENV_STEP * env_steps_per_launch / (kern_ms_max * 1e-3) / 1e9 / peak,
+                              "kernel": kernel_name, "n_envs": n, "status_max": int(env.status.max())}), flush=True)
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
     # ---- end-to-end through the public API with HOST buffers (pinned): H2D actions, D2H obs/reward/done
     a_host = [r.cpu().pin_memory() for r in ring[:2]]
-    out_host = None
-    out_sets = [None, None]
-    def one_e2e(i):
-        # public API with host buffers: actions H2D, kernel(s), obs/reward/done D2H of THIS step, all enqueued here.
-        # wait=False lets step i+1's upload overlap step i's download (two result sets alternate); env.host_sync()
-        # before the closing barrier completes every step inside the timed region.
-        nonlocal out_host
-        env.rewind()
-        out_sets[i % 2] = out_host = env.rollout_host(a_host[i % 2], out=out_sets[i % 2], chunks=args.e2e_chunks, wait=False)
-        return out_host
-    Ke = max(3, min(K, 10))
-    for i in range(2):
-        one_e2e(i)
-    env.host_sync()
-    barrier()
-    t0 = time.perf_counter()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(Ke):
-        one_e2e(i)
-    env.host_sync()                                   # every step's results are in host memory
-    e1.record()
-    barrier()
-    e2e_ms = sharding.max_over_ranks(e0.elapsed_time(e1), dev)
-    e2e_value = world * env_steps_per_launch * Ke / (e2e_ms * 1e-3)
+
+    def run_e2e(outputs):
+        """Ke steps of make_env.rollout_host: actions H2D, kernel(s), results D2H, all enqueued per step; wait=False
+        lets step i+1's upload overlap step i's download (two result sets alternate); host_sync() before the closing
+        event completes every step inside the timed region."""
+        sets, last = [None, None], None
+
+        def one(i):
+            nonlocal last
+            env.rewind()
+            sets[i % 2] = last = env.rollout_host(a_host[i % 2], out=sets[i % 2], chunks=args.e2e_chunks, wait=False,
+                                                  outputs=outputs)
+        Ke = max(3, min(K, 10))
+        for i in range(2):
+            one(i)
+        env.host_sync()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(Ke):
+            one(i)
+        env.host_sync()                                   # every step's results are in host memory
+        e1.record()
+        barrier()
+        ms = sharding.max_over_ranks(e0.elapsed_time(e1), dev)
+        d2h = sum(v.numel() * v.element_size() for v in last.values())
+        return world * env_steps_per_launch * Ke / (ms * 1e-3), ms / Ke, d2h, Ke
+
+    e2e_value, e2e_ms, d2h, Ke = run_e2e(None)
+    red_value, red_ms, red_d2h, _ = run_e2e(("return", "obs_last", "done"))
     h2d = a_host[0].numel() * 8
-    d2h = sum(v.numel() * v.element_size() for v in out_host.values())
+
+    # pinned device->host copy ceiling at THIS rank count (all ranks copy at once): what any e2e number that brings
+    # d2h bytes per step back to the host is bounded by
+    src = torch.empty(d2h // 8, dtype=torch.float64, device=dev)
+    dst = torch.empty(d2h // 8, dtype=torch.float64).pin_memory()
+    dst.copy_(src, non_blocking=True)
+    barrier()
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    c0.record()
+    for _ in range(5):
+        dst.copy_(src, non_blocking=True)
+    c1.record()
+    barrier()
+    copy_ms = sharding.max_over_ranks(c0.elapsed_time(c1) / 5, dev)
+    d2h_ceiling = d2h / (copy_ms * 1e-3) / 1e9            # GB/s per rank, slowest rank
+    del src, dst
 
     # ---- Gym-style step mode (one interval per launch), information only
     env.reset()
@@ -298,32 +413,46 @@ def main():
         return
     peak, peak_src = hbm_peak()
     achieved = BYTES_PER_ENV_STEP * env_steps_per_launch / (kern_ms_max * 1e-3) / 1e9
+    traffic, traffic_src = ncu_traffic() if n == N_ENVS else (None, None)
     line = {
         "metric": "env-steps/s", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": "BASELINE config 3: CSTR, 65 536 envs per GPU x 99 control intervals per launch "
-                               "(N=100, dt=0.25), Gaussian noise 0.1 % (Philox, fp64 Box-Muller), constraints "
+                               "(N=100, dt=0.25), Gaussian noise 0.1 % (Philox4x32-10, fp64 inverse-CDF draw), constraints "
                                "319<=T<=331 with r_penalty, SP reward, normalised obs",
                    "n_envs_per_gpu": n, "intervals_per_launch": K_STEPS, "integrator": HEADLINE_INTEGRATOR,
-                   "parity": "rtol 1e-6 vs converged oracle at this size: tests/test_gpu_parity.py::test_headline_config_full_size_rtol_1e6",
+                   "parity": "this exact kernel x size x noise against the oracle (x same-scheme 1e-11 and converged 1e-6, "
+                             "obs with the documented draw, reward, flags): tests/test_gpu_parity.py::"
+                             "test_headline_config_full_size_noise_on",
+                   "timed_region": ("one replay of a CUDA graph holding the K launches" if graph is not None
+                                    else "K eager launches"),
                    "l2": "inputs+outputs per launch ~0.48 GB > 126 MB L2; action buffers rotate over a ring of 3",
                    "parallelism": f"env-sharded x{world}, no collective" +
-                                  (f"; ranks bound to their GPU's NUMA CPUs ({len(numa_cpus)} on rank 0)" if numa_cpus else "")},
+                                  (f"; each rank bound to its own slice of its GPU's NUMA CPUs ({len(numa_cpus)} on rank 0)"
+                                   if numa_cpus else "")},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "frac_of_nominal_8000": achieved / 8000.0,
-                     "traffic": NCU_DRAM_BYTES_PER_LAUNCH if n == N_ENVS else None,
-                     "traffic_note": "dram__bytes_read+write.sum of one launch, profiles/r1_cstr_v8_wsm_ncu_summary.txt "
-                                     "(~55 MB of the stores are still in L2 at kernel end)",
+                     "traffic": traffic,
+                     "traffic_note": f"dram__bytes_read+write.sum of one launch, {traffic_src} "
+                                     "(part of the stores is still in L2 at kernel end)" if traffic else None,
                      "algorithmic_bytes": BYTES_PER_ENV_STEP * env_steps_per_launch,
                      "peak_source": peak_src, "bytes_per_env_step": BYTES_PER_ENV_STEP,
                      "kernel_ms": kern_ms_max, "kernel": kernel_name,
-                     "fp64_note": "instruction-issue / FP64-pipe bound, not HBM bound: ~250 FP64 + ~225 other instructions per env-step against 74 B (profiles/README.md, DESIGN.md section 5)"},
+                     "fp64_note": "issue / FP64-pipe bound, not HBM bound (profiles/README.md, DESIGN.md section 5)"},
         "cpu_baseline": cpu,
         "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "steps": Ke, "ms_per_step": e2e_ms / Ke},
+                "steps": Ke, "ms_per_step": e2e_ms,
+                "d2h_ceiling_gbs_per_rank": d2h_ceiling,
+                "d2h_achieved_gbs_per_rank": d2h / (e2e_ms * 1e-3) / 1e9,
+                "frac_of_d2h_ceiling": (d2h / (e2e_ms * 1e-3) / 1e9) / d2h_ceiling,
+                "ceiling_note": f"plain pinned device->host copy of the same {d2h} bytes, all {world} ranks at once, slowest rank",
+                "reduced": {"value": red_value, "unit": "env-steps/s", "ms_per_step": red_ms,
+                            "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": red_d2h,
+                            "outputs": ["return", "obs_last", "done"]}},
         "gpu_launches": int(launches),
-        "clocks": clk.summary(),
+        "per_rank": {"columns": ["graph_ms_per_step", "eager_kernel_ms", "host_enqueue_us_per_launch"], "rows": per_rank},
+        "clocks": clk.summary(c_lo, c_hi),
         "step_mode": {"env_steps_per_s": n / (step_ms * 1e-3), "ms_per_step": step_ms,
                       "note": "make_env.step(): one control interval per launch incl. torch-side copies"},
     }

@@ -26,6 +26,7 @@ def cstr_headline_params(N=100):
         "noise": True, "noise_percentage": 0.001,
         "constraints": lambda x, u: np.array([319 - x[1], x[1] - 331]).reshape(-1,),
         "done_on_cons_vio": False, "r_penalty": True,
+        "constraint_units": "physical",        # as the GPU arm: g sees physical T (bench.py cstr_headline)
         "normalise_a": True, "normalise_o": True,
     }
 

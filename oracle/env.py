@@ -11,6 +11,9 @@ Differences from the reference that are deliberate and visible:
     source) so tests can replay recorded draws.
   * `integrator` selects "truth" (DOP853 1e-12), "lsoda" (CVODES-default
     stand-in, for timing) or "dense" (RK4 x n_sub).
+  * `env_params["constraint_units"] = "physical"` (the same opt-in the CUDA
+    env offers) skips constraint_check's un-normalisation of values that are
+    already physical (pcgym.py:597-608); the default replicates it.
 """
 from __future__ import annotations
 
@@ -333,9 +336,10 @@ class OracleEnv:
     # -- constraints (pcgym.py:560-615) ---------------------------------------
     def constraint_check(self, state, inputs):
         P = self.env_params
-        if self.normalise_a is True:          # un-normalises values that are already physical (:597-600)
+        quirk = P.get("constraint_units", "reference") == "reference"
+        if self.normalise_a is True and quirk:   # un-normalises values that are already physical (:597-600)
             inputs = (inputs + 1) * (P["a_space"]["high"] - P["a_space"]["low"]) / 2 + P["a_space"]["low"]
-        if self.normalise_o is True:                                            # :602-608
+        if self.normalise_o is True and quirk:                                  # :602-608
             lo, hi = self.observation_space_base.low, self.observation_space_base.high
             state = (state + 1) * (hi - lo) / 2 + lo
         g = np.asarray(self.constraints(state, inputs), dtype=np.float64)

@@ -135,6 +135,8 @@ def lib():
         try:
             fn = getattr(L, name)
         except AttributeError as e:
+            if os.environ.get("PCG_LIB") and name == "pcg_set_kernel":
+                continue                    # A/B profiling against a library built before the knob existed
             raise NativeError(f"{LIB_PATH} does not export {name}") from e
         fn.restype, fn.argtypes = res, args
     if L.pcg_abi_version() != ABI_VERSION:

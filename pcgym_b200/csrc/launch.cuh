@@ -187,6 +187,7 @@ template <class M, class TB, int NOISE, int NSP, bool CONU, bool SPS>
 cudaError_t launch_wsm_n(const pcg_desc& d, const pcg_io& io, const Derived<M, TB>& dv, int64_t n_env, int t0,
                          int k_steps, cudaStream_t s, int64_t epc, int n_tiles) {
   using Shared = WsmShared<M, NOISE, NSP, SPS>;
+  static_assert(sizeof(Shared) <= 227 * 1024, "wsm_rollout_kernel: rings + tables exceed the 227 KB a CTA may opt in to");
   // > 48 KB of dynamic shared memory needs the opt-in, once per kernel instantiation AND device
   static std::atomic<uint64_t> opted{0};
   int dev = 0;

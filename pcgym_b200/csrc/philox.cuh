@@ -44,32 +44,38 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, const PhiloxKeys& rk) {
 // Draw layout (all kernels, all shardings): one Philox block serves the env PAIR (gid >> 1) at time t for the
 // state pair j; env (gid & 1) takes words (x, y) or (z, w); word k of the two is the draw of state 2j + k:
 //     z = Phi^-1(u),  u = (w + 1/2) 2^-32          (inverse normal CDF of a 32-bit uniform: |z| <= 6.34)
-// evaluated in fp64 by a table of piecewise degree-7 polynomials (csrc/icdftab.inc, tools/gen_icdf_tab.py):
+// evaluated in fp64 by a table of piecewise degree-5 polynomials (csrc/icdftab.inc, tools/gen_icdf_tab.py):
 //     fold     w >= 2^31: w' = ~w and the sign flips      p = (w' + 1/2) 2^-32 = m 2^-33,  m = 2 w' + 1
-//     segment  b = leading-one index of m, sub = its next three bits          256 segments of 8 coefficients
+//     segment  b = leading-one index of m, sub = its next four bits           512 segments of 6 coefficients
 //     local    v = the remaining bits of m, centred, as a signed 32-bit integer (coefficients are pre-scaled)
-// 1 conversion + 7 DFMA per draw (the Box-Muller it replaced cost 36 FP64 instructions per pair of draws and two
-// table lookups on its critical path); maximum absolute error 5.8e-14 against scipy.special.ndtri, where adjacent
+// 1 conversion + 5 DFMA + three 128-bit shared-memory loads per draw (the Box-Muller it replaced cost 36 FP64
+// instructions per pair of draws); maximum absolute error 1.7e-12 against scipy.special.ndtri, where adjacent
 // 32-bit uniforms are >= 5.8e-10 apart in z -- the transform is exact at the resolution of its input.
-// `tab` is kIcdfTab or a shared-memory copy of it.
+// `tab` is a shared-memory copy of kIcdfTab (kIcdfTab itself only in pcg_normal_pairs).
 
-static __device__ const double kIcdfTab[256 * 8] = {
+constexpr int kIcdfDoubles = 512 * 6;
+static __device__ const double kIcdfTab[kIcdfDoubles] = {
 #include "icdftab.inc"
 };
+
+// Every kernel family reads the table from SHARED memory: four 128-bit loads per draw with a different segment in
+// every lane are ~32 L1 tag look-ups each from global memory (measured: the pair-per-CTA kernel went from 0.342 to
+// 0.432 ms at 131 072 envs with the table in global memory), but only bank conflicts in shared memory.
+PCG_DEV void fill_icdf_tab(double* tab) {          // whole CTA; the caller synchronises
+  for (int i = threadIdx.x; i < kIcdfDoubles; i += blockDim.x) tab[i] = kIcdfTab[i];
+}
 
 PCG_DEV double normal_icdf_u32(uint32_t w, const double* tab) {
   const int s = static_cast<int>(w) >> 31;                             // all ones: upper half of the uniform
   const uint32_t m = ((w ^ static_cast<uint32_t>(s)) << 1) | 1u;
   const int lz = __clz(m);
   const uint32_t mn = m << lz;                                         // leading one at bit 31
-  const uint32_t seg = static_cast<uint32_t>(31 - lz) * 8u + (mn >> 28);   // + 8: taken off the base below
-  const int v = static_cast<int>((mn << 4) ^ 0x80000000u);
+  const uint32_t seg = static_cast<uint32_t>(31 - lz) * 16u + (mn >> 27);  // + 16: taken off the base below
+  const int v = static_cast<int>((mn << 5) ^ 0x80000000u);
   const double x = static_cast<double>(v);
-  const double2* c = reinterpret_cast<const double2*>(tab) + (static_cast<int>(seg) - 8) * 4;
-  const double2 c01 = c[0], c23 = c[1], c45 = c[2], c67 = c[3];
-  double z = fma(c67.y, x, c67.x);
-  z = fma(z, x, c45.y);
-  z = fma(z, x, c45.x);
+  const double2* c = reinterpret_cast<const double2*>(tab) + (static_cast<int>(seg) - 16) * 3;
+  const double2 c01 = c[0], c23 = c[1], c45 = c[2];
+  double z = fma(c45.y, x, c45.x);
   z = fma(z, x, c23.y);
   z = fma(z, x, c23.x);
   z = fma(z, x, c01.y);

@@ -34,6 +34,11 @@ __global__ void __launch_bounds__(kBlock, EPT == 1 ? M::MIN_BLOCKS_EPT1 : M::MIN
 fast_rollout_kernel(const __grid_constant__ pcg_desc d, const __grid_constant__ pcg_io io,
                     const __grid_constant__ Derived<M, TB> dv, const int64_t n, const int t0, const int k_steps) {
   constexpr int NX = M::NX, NU = M::NU, ND = M::ND, NUK = NU + ND;
+  __shared__ __align__(16) double icdf_s[NOISE == PCG_NOISE_PHILOX ? kIcdfDoubles : 2];
+  if constexpr (NOISE == PCG_NOISE_PHILOX) {
+    fill_icdf_tab(icdf_s);
+    __syncthreads();
+  }
   const int64_t env0 = (static_cast<int64_t>(blockIdx.x) * kBlock + threadIdx.x) * EPT;
   if (env0 >= n) return;
 
@@ -212,7 +217,7 @@ fast_rollout_kernel(const __grid_constant__ pcg_desc d, const __grid_constant__ 
 #pragma unroll
       for (int i = 0; i < NX; i += 2) {
         double za[EPT], zb[EPT];
-        draw_state_pair<EPT, NOISE == PCG_NOISE_PHILOX_F32>(gid0, static_cast<uint32_t>(cur.t_new), i / 2, key, kIcdfTab, za, zb);
+        draw_state_pair<EPT, NOISE == PCG_NOISE_PHILOX_F32>(gid0, static_cast<uint32_t>(cur.t_new), i / 2, key, icdf_s, za, zb);
 #pragma unroll
         for (int e = 0; e < EPT; ++e) {
           cur.z[e][i] = za[e];

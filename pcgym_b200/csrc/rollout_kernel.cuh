@@ -251,6 +251,11 @@ rollout_kernel(const __grid_constant__ pcg_desc d, const __grid_constant__ pcg_i
   constexpr int NDOM = GENERAL ? PCG_MAX_ND : 1;
   constexpr int NTLM = GENERAL ? PCG_MAX_NTAIL : 1;
   constexpr int NCONM = GENERAL ? PCG_MAX_NCON : 4;            // constraints handled by this instantiation
+  __shared__ __align__(16) double icdf_s[kIcdfDoubles];        // inverse-normal-CDF table (philox.cuh)
+  if (d.noise == PCG_NOISE_PHILOX) {                           // uniform: the whole CTA takes the same path
+    fill_icdf_tab(icdf_s);
+    __syncthreads();
+  }
   const int64_t env0 = (static_cast<int64_t>(blockIdx.x) * kBlock + threadIdx.x) * EPT;
   if (env0 >= n) return;                                       // EPT == 2 implies even n: both envs valid
 
@@ -513,8 +518,8 @@ rollout_kernel(const __grid_constant__ pcg_desc d, const __grid_constant__ pcg_i
 #pragma unroll
         for (int i = 0; i < NX; i += 2) {
           double za[EPT], zb[EPT];
-          if (noise == PCG_NOISE_PHILOX) draw_state_pair<EPT, false>(gid0, static_cast<uint32_t>(t_new), i / 2, key, kIcdfTab, za, zb);
-          else draw_state_pair<EPT, true>(gid0, static_cast<uint32_t>(t_new), i / 2, key, kIcdfTab, za, zb);
+          if (noise == PCG_NOISE_PHILOX) draw_state_pair<EPT, false>(gid0, static_cast<uint32_t>(t_new), i / 2, key, icdf_s, za, zb);
+          else draw_state_pair<EPT, true>(gid0, static_cast<uint32_t>(t_new), i / 2, key, icdf_s, za, zb);
 #pragma unroll
           for (int e = 0; e < EPT; ++e) {
             z[e][i] = za[e];

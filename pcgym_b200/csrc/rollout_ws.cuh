@@ -31,14 +31,43 @@ PCG_DEV void mbar_init(uint64_t* b, int count) {
 PCG_DEV void mbar_arrive(uint64_t* b) {          // release.cta: this lane's earlier smem writes are visible to waiters
   asm volatile("{\n .reg .b64 st;\n mbarrier.arrive.shared::cta.b64 st, [%0];\n}" ::"r"(smem_u32(b)) : "memory");
 }
-PCG_DEV void mbar_wait(uint64_t* b, uint32_t parity) {   // acquire.cta; try_wait suspends the warp in hardware
+PCG_DEV bool mbar_try(uint64_t* b, uint32_t parity) {
+  uint32_t ok;
+  asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+               : "=r"(ok)
+               : "r"(smem_u32(b)), "r"(parity)
+               : "memory");
+  return ok != 0;
+}
+PCG_DEV void mbar_wait(uint64_t* b, uint32_t parity) {   // acquire.cta; retries spin (pair-per-CTA kernel: waits are rare)
+  while (!mbar_try(b, parity)) {}
+}
+// The same wait for the per-SM kernel, where one of the two roles is ahead of the other most of the time: measured
+// (ncu source page, profiles/README.md r2) try_wait comes back within ~7 cycles, and the retry loops of the waiting
+// role issued 34 M of the kernel's 87 M warp instructions -- issue slots taken from the role that sets the pace.
+// So a failed first try backs off: PCG_WSM_WAIT 1 = nanosleep between tries (the warp leaves the scheduler),
+// 2 = try_wait with a suspend-time hint, 0 = spin (A/B).
+#ifndef PCG_WSM_WAIT
+#define PCG_WSM_WAIT 1
+#endif
+#ifndef PCG_WSM_SLEEP_NS
+#define PCG_WSM_SLEEP_NS 64
+#endif
+PCG_DEV void mbar_wait_backoff(uint64_t* b, uint32_t parity) {
+  if (mbar_try(b, parity)) return;
+#if PCG_WSM_WAIT == 1
+  do { __nanosleep(PCG_WSM_SLEEP_NS); } while (!mbar_try(b, parity));
+#elif PCG_WSM_WAIT == 2
   uint32_t ok;
   do {
-    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n selp.u32 %0, 1, 0, p;\n}"
                  : "=r"(ok)
-                 : "r"(smem_u32(b)), "r"(parity)
+                 : "r"(smem_u32(b)), "r"(parity), "r"(0x989680)
                  : "memory");
   } while (!ok);
+#else
+  while (!mbar_try(b, parity)) {}
+#endif
 }
 
 // models whose integrator-warp RHS reads the shared-memory 2^(j/256) table (exp_tab_split): M::EXP_TAB
@@ -74,7 +103,9 @@ ws_rollout_kernel(const __grid_constant__ pcg_desc d, const __grid_constant__ pc
   constexpr int NX = M::NX, NU = M::NU, ND = M::ND, NUK = NU + ND, EPT = 2, R = kWsRing;
   __shared__ __align__(16) WsPair<M> sm[W];
   __shared__ double exp_tab[uses_exp_tab<M>::value ? 256 : 1];
+  __shared__ __align__(16) double icdf_s[NOISE == PCG_NOISE_PHILOX ? kIcdfDoubles : 2];
   fill_exp_tab<M>(exp_tab);
+  if constexpr (NOISE == PCG_NOISE_PHILOX) fill_icdf_tab(icdf_s);
   // Role placement.  A warp's scheduler (SM sub-partition) is its hardware slot %warpid mod 4 and the CTAs of an
   // SM occupy consecutive slots, so a fixed (integrator, finisher) order would put every integrator warp -- the
   // FP64-heavy role -- on the same two sub-partitions.  Warp 2p / 2p+1 form pair p; which of the two integrates
@@ -302,7 +333,7 @@ ws_rollout_kernel(const __grid_constant__ pcg_desc d, const __grid_constant__ pc
 #pragma unroll
       for (int i = 0; i < NX; i += 2) {
         double za[EPT], zb[EPT];
-        draw_state_pair<EPT, NOISE == PCG_NOISE_PHILOX_F32>(gid0, static_cast<uint32_t>(t_new), i / 2, key, kIcdfTab, za, zb);
+        draw_state_pair<EPT, NOISE == PCG_NOISE_PHILOX_F32>(gid0, static_cast<uint32_t>(t_new), i / 2, key, icdf_s, za, zb);
 #pragma unroll
         for (int e = 0; e < EPT; ++e) {
           z[e][i] = za[e];

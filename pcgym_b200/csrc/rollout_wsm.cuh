@@ -12,20 +12,69 @@
 //     the load evens out across the four schedulers without any static partition.
 // A task is stateless given (p, k) as long as `done` does not depend on earlier violations, so the kernel requires
 // done_on_cons_vio == False (the launcher falls back otherwise).  Same ring / mbarrier hand-over as rollout_ws.cuh.
+//
+// Round 2 (profiles/README.md "r2"): the ncu source page showed the kernel bound by LATENCY, not by issue slots or the
+// FP64 pipe (both ~50 % busy): 16 resident warps, each a dependent chain with ILP ~2, cannot cover 8-cycle DFMA
+// dependencies, ~30-cycle shared-memory and ~1000-cycle global loads.  Removing a quarter of the FP64 instructions
+// changed the time by 4 %.  So the integrators now carry ONE env per lane and there are twice as many of them
+// (two integrator warps per 64-env tile, lane L of warp h owns env 2L + h of the tile): 14 + 6 = 20 warps of <= 96
+// registers per SM at the headline batch, 3.5 integrator chains per scheduler instead of 1.75; and the action rows
+// reach the ring by cp.async (global -> shared, completion signalled on the tile's mbarrier), so no finisher ever
+// waits on a global load.
 #pragma once
 #include "rollout_ws.cuh"
 
 namespace pcg {
 
-constexpr int kWsmWarps = 16;      // 512 threads, 128 registers: one CTA fills an SM
-constexpr int kWsmMaxTiles = 8;    // integrator warps per CTA (<= 512 envs per SM)
+#ifndef PCG_WSM_EPI
+#define PCG_WSM_EPI 1              // envs per integrator lane (2 = the round-1 layout, kept for A/B)
+#endif
+// Warp layout of the CTA.  With PCG_WSM_INT_REGS != 0 the first 16 warps (four warpgroups) are the integrator class
+// and give registers back (setmaxnreg.dec) which the finisher warpgroups behind them take (setmaxnreg.inc): ptxas
+// needs 54 registers for the one-env integrator and ~74-92 for the finisher, so the register file holds
+//   24 warps: 16 x 56 + 8 x 96        28 warps: 16 x 56 + 12 x 88        32 warps: 16 x 56 + 16 x 72
+// With PCG_WSM_INT_REGS == 0 every warp keeps the launch budget, integrators first, the rest finishers (A/B: 20 warps x 96).
+#ifndef PCG_WSM_WARPS
+#define PCG_WSM_WARPS 28
+#endif
+#ifndef PCG_WSM_INT_REGS
+#define PCG_WSM_INT_REGS 56
+#endif
+#ifndef PCG_WSM_FIN_REGS
+#define PCG_WSM_FIN_REGS 88
+#endif
+#ifndef PCG_WSM_PREFETCH
+#define PCG_WSM_PREFETCH 1         // take the next task id while the current task runs (hides the shared-memory atomic)
+#endif
+constexpr int kWsmEpi = PCG_WSM_EPI;
+constexpr int kWsmIpt = 2 / kWsmEpi;                       // integrator warps per 64-env tile
+constexpr int kWsmWarps = kWsmEpi == 2 ? 16 : PCG_WSM_WARPS;
+constexpr int kWsmIntClass = (kWsmEpi == 1 && PCG_WSM_INT_REGS != 0) ? 16 : 0;   // warps [0, 16) hold the small register budget
+constexpr int kWsmLaunchRegs = (65536 / (32 * kWsmWarps)) / 8 * 8;
+static_assert(kWsmIntClass == 0 ||
+              16 * (kWsmLaunchRegs - PCG_WSM_INT_REGS) >= (kWsmWarps - 16) * (PCG_WSM_FIN_REGS - kWsmLaunchRegs),
+              "setmaxnreg budgets do not fit the register file");
+constexpr int kWsmMaxTiles = 8;    // 64-env tiles per CTA (<= 512 envs per SM)
+static_assert(kWsmIntClass == 0 || kWsmIntClass >= kWsmMaxTiles * kWsmIpt, "integrator class must hold every integrator warp");
 // Ring depth.  An mbarrier wait names its phase by PARITY only, so a waiter may never be a whole phase ahead of the
 // barrier.  A finisher holding interval k + RING of a tile while interval k of the same tile is still waiting for the
 // integrator would be exactly that; all the intervals in between would be outstanding too, i.e. RING + 1 finishers
-// stuck on one tile.  With RING >= the number of finishers (<= 14) that cannot happen, so no further ordering is
-// needed between finishers (an earlier version with RING = 8 had to serialise tasks per slot with a counter).
+// stuck on one tile.  With RING >= the number of finishers (capped at kWsmMaxFin) that cannot happen, so no further
+// ordering is needed between finishers (an earlier version with RING = 8 had to serialise tasks per slot with a counter).
 constexpr int kWsmRing = 16;
-static_assert(kWsmRing >= kWsmWarps - 2 && (kWsmRing & (kWsmRing - 1)) == 0, "ring depth vs finisher count");
+constexpr int kWsmMaxFin = 16;
+static_assert(kWsmRing >= kWsmMaxFin && (kWsmRing & (kWsmRing - 1)) == 0, "ring depth vs finisher count");
+
+template <int N> PCG_DEV void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N> PCG_DEV void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+
+PCG_DEV void cp_async16(void* smem, const void* gmem) {          // 16 bytes global -> shared, no register staging
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem)), "l"(gmem) : "memory");
+}
+// arrive on `b` once every cp.async this thread issued before has landed (counts as one of the expected arrivals)
+PCG_DEV void cp_async_arrive(uint64_t* b) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(b)) : "memory");
+}
 
 constexpr int kWsmSpMax = 256;     // staged setpoint schedule: k_steps + 1 <= kWsmSpMax time indices per setpoint
 
@@ -37,7 +86,7 @@ struct WsmShared {
   uchar2 done0[kWsmMaxTiles][32];   // sticky done flag each env entered the launch with
   int next_task;
   double exp_tab[uses_exp_tab<M>::value ? 256 : 1];   // 2^(j/256) for exp_tab_split (integrator warps)
-  double icdf[NOISE == PCG_NOISE_PHILOX ? 256 * 8 : 2];   // kIcdfTab (finishers)
+  alignas(16) double icdf[NOISE == PCG_NOISE_PHILOX ? kIcdfDoubles : 2];   // kIcdfTab (finishers; read as double2)
   double sp[SPS ? NSP : 1][SPS ? kWsmSpMax : 1];      // SP[j][t0 + i], i = 0..k_steps
 };
 
@@ -63,18 +112,20 @@ wsm_rollout_kernel(const __grid_constant__ pcg_desc d, const __grid_constant__ p
     const int left = cta_pairs - p * 32;
     return left < 0 ? 0 : (left > 32 ? 32 : left);
   };
+  constexpr int EPI = kWsmEpi, IPT = kWsmIpt;
+  const int n_int = n_tiles * IPT;                                             // integrator warps of this CTA
   if (warp < n_tiles && lane == 0) {
     const int cnt = tile_lanes(warp) > 0 ? tile_lanes(warp) : 1;
 #pragma unroll
     for (int s = 0; s < R; ++s) {
-      mbar_init(&sh.tile[warp].full_a[s], cnt);
-      mbar_init(&sh.tile[warp].full_x[s], cnt);
+      mbar_init(&sh.tile[warp].full_a[s], cnt);                                // one cp.async arrival per finisher lane
+      mbar_init(&sh.tile[warp].full_x[s], cnt * IPT);                          // one arrival per integrator lane
     }
   }
   if (threadIdx.x == 0) sh.next_task = 0;
   fill_exp_tab<M>(sh.exp_tab);
   if constexpr (NOISE == PCG_NOISE_PHILOX) {
-    for (int i = threadIdx.x; i < 256 * 8; i += blockDim.x) sh.icdf[i] = kIcdfTab[i];
+    fill_icdf_tab(sh.icdf);
   }
   if constexpr (SPS) {               // SP[j][t0 .. t0 + k_steps] (t0 + k_steps <= N - 1: abi.cu validates)
     for (int i = threadIdx.x; i < NSP * (k_steps + 1); i += blockDim.x) {
@@ -94,66 +145,71 @@ wsm_rollout_kernel(const __grid_constant__ pcg_desc d, const __grid_constant__ p
     }
   };
 
-  if (warp < n_tiles) {
-    // ================================================================ integrator warp of tile `warp`
-    if (lane >= tile_lanes(warp)) return;
-    WsPair<M, R>& sp = sh.tile[warp];
-    const int64_t env0 = cta_base + static_cast<int64_t>(warp) * 64 + 2 * lane;
-    double x[EPT][NX];
+  // first finisher warp / number of finishers (warps between the two roles, and past the last finisher, retire)
+  const int fin0 = kWsmIntClass ? kWsmIntClass : n_int;
+  const int n_fin = (kWsmWarps - fin0) < kWsmMaxFin ? (kWsmWarps - fin0) : kWsmMaxFin;
+  if (warp < fin0) {
+    if constexpr (kWsmIntClass != 0) setmaxnreg_dec<PCG_WSM_INT_REGS>();                     // whole warpgroups: warps 0..15
+    if (warp >= n_int) return;
+    // ================================================================ integrator warp: tile p, env 2 lane + h (+ e)
+    const int p = warp / IPT, h = (warp % IPT) * EPI;
+    if (lane >= tile_lanes(p)) return;
+    WsPair<M, R>& sp = sh.tile[p];
+    const int64_t env0 = cta_base + static_cast<int64_t>(p) * 64 + 2 * lane + h;
+    double x[EPI][NX];
 #pragma unroll
     for (int i = 0; i < NX; ++i) {
-      double v[EPT];
-      ld_row<EPT>(io.x + i * n + env0, v);
+      double v[EPI];
+      ld_row<EPI>(io.x + i * n + env0, v);
 #pragma unroll
-      for (int e = 0; e < EPT; ++e) x[e][i] = v[e];
+      for (int e = 0; e < EPI; ++e) x[e][i] = v[e];
     }
     // the finishers read the initial state for the t == 0 pre-check before they release interval 0, so io.x may be
     // overwritten at the end without a race
 #pragma unroll 1
     for (int k = 0; k < k_steps; ++k) {
       const int s = k & (R - 1);
-      mbar_wait(&sp.full_a[s], (k / R) & 1);
-      double a_raw[NU][EPT];
+      mbar_wait_backoff(&sp.full_a[s], (k / R) & 1);
+      double uk[EPI][NUK];
 #pragma unroll
-      for (int j = 0; j < NU; ++j) {
-        const double2 t = sp.a[s][j][lane];
-        a_raw[j][0] = t.x;
-        a_raw[j][1] = t.y;
+      for (int e = 0; e < EPI; ++e) {                                          // pcgym.py:372-375, 386-414
+#pragma unroll
+        for (int j = 0; j < NU; ++j)
+          uk[e][j] = fma(reinterpret_cast<const double*>(&sp.a[s][j][lane])[h + e], d.a_scale[j], d.a_off[j]);
+#pragma unroll
+        for (int i = 0; i < ND; ++i) uk[e][NU + i] = d.d_default[i];
       }
-      double uk[EPT][NUK];
-      to_uk(a_raw, uk);
-      typename M::Aux aux[EPT];
+      typename M::Aux aux[EPI];
 #pragma unroll
-      for (int e = 0; e < EPT; ++e) {
+      for (int e = 0; e < EPI; ++e) {
         M::prep(dv.p, uk[e], aux[e]);
         bind_exp_tab<M>(aux[e], sh.exp_tab);
       }
-      rk_step_fixed<M, TB, EPT>(dv, aux, x, uk);                               // integrator.py:90-107
+      rk_step_fixed<M, TB, EPI>(dv, aux, x, uk);                               // integrator.py:90-107
 #pragma unroll
-      for (int i = 0; i < NX; ++i) sp.x[s][i][lane] = make_double2(x[0][i], x[1][i]);
+      for (int i = 0; i < NX; ++i)
+#pragma unroll
+        for (int e = 0; e < EPI; ++e) reinterpret_cast<double*>(&sp.x[s][i][lane])[h + e] = x[e][i];
       mbar_arrive(&sp.full_x[s]);
     }
-    unsigned status[EPT] = {0, 0};
 #pragma unroll
-    for (int i = 0; i < NX; ++i) {
-      double v[EPT];
+    for (int e = 0; e < EPI; ++e) {
+      unsigned status = 0;
 #pragma unroll
-      for (int e = 0; e < EPT; ++e) {
-        v[e] = x[e][i];
-        if (!isfinite(v[e])) status[e] |= PCG_ST_NONFINITE;
+      for (int i = 0; i < NX; ++i) {
+        if (!isfinite(x[e][i])) status |= PCG_ST_NONFINITE;
+        io.x[i * n + env0 + e] = x[e][i];
       }
-      st_row<EPT>(io.x + i * n + env0, v);
-    }
-#pragma unroll
-    for (int e = 0; e < EPT; ++e) {
-      if (io.status && status[e]) io.status[env0 + e] |= static_cast<uint8_t>(status[e]);
+      if (io.status && status) io.status[env0 + e] |= static_cast<uint8_t>(status);
       if (io.n_rhs) io.n_rhs[env0 + e] += k_steps * TB::S;
     }
     return;
   }
 
   // ================================================================== finisher pool
-  const int fin = warp - n_tiles, n_fin = kWsmWarps - n_tiles;
+  if constexpr (kWsmIntClass != 0) setmaxnreg_inc<PCG_WSM_FIN_REGS>();                       // whole warpgroups: warps 16 and up
+  const int fin = warp - fin0;
+  if (fin >= n_fin) return;
   const int flags = d.flags;
   const int nsp = d.nsp, n_con = d.n_con;
   const int nsp_obs = (flags & PCG_F_SP_HIDDEN) ? 0 : nsp, n_obs = NX + nsp_obs;
@@ -217,12 +273,8 @@ wsm_rollout_kernel(const __grid_constant__ pcg_desc d, const __grid_constant__ p
     for (int s = 0; s < R; ++s) {
       if (s < k_steps) {
 #pragma unroll
-        for (int j = 0; j < NU; ++j) {
-          double v[EPT];
-          ld_row<EPT>(pa + (static_cast<int64_t>(s) * NU + j) * n, v);
-          sp.a[s][j][lane] = make_double2(v[0], v[1]);
-        }
-        mbar_arrive(&sp.full_a[s]);
+        for (int j = 0; j < NU; ++j) cp_async16(&sp.a[s][j][lane], pa + (static_cast<int64_t>(s) * NU + j) * n);
+        cp_async_arrive(&sp.full_a[s]);
       }
     }
   }
@@ -232,11 +284,21 @@ wsm_rollout_kernel(const __grid_constant__ pcg_desc d, const __grid_constant__ p
   // floor(q / n_tiles) = umulhi(q, ceil(2^32 / n_tiles)) for q < 2^32 / n_tiles (n_tiles <= 8, q < 2^27: launch.cuh)
   const uint32_t tiles_rcp = static_cast<uint32_t>((uint64_t{1} << 32) / static_cast<uint32_t>(n_tiles)) + 1u;
 #pragma unroll 1
+#if PCG_WSM_PREFETCH
+  int q_nxt = 0;
+  if (lane == 0) q_nxt = atomicAdd(&sh.next_task, 1);
+#endif
   while (true) {
+#if PCG_WSM_PREFETCH
+    const int q = __shfl_sync(0xffffffffu, q_nxt, 0);
+    if (q >= n_tasks) break;
+    if (lane == 0) q_nxt = atomicAdd(&sh.next_task, 1);                        // consumed one iteration later
+#else
     int q = 0;
     if (lane == 0) q = atomicAdd(&sh.next_task, 1);
     q = __shfl_sync(0xffffffffu, q, 0);
     if (q >= n_tasks) break;
+#endif
     const int k = static_cast<int>(__umulhi(static_cast<uint32_t>(q), tiles_rcp)), p = q - k * n_tiles;   // q / n_tiles
     if (lane >= tile_lanes(p)) continue;
     WsPair<M, R>& sp = sh.tile[p];
@@ -245,12 +307,7 @@ wsm_rollout_kernel(const __grid_constant__ pcg_desc d, const __grid_constant__ p
     const uint32_t env0 = static_cast<uint32_t>(cta_base) + static_cast<uint32_t>(p) * 64u + 2u * lane;
     const uint32_t kn = static_cast<uint32_t>(k) * n32;
 
-    // action rows of interval k + R for this tile (row clamped at the last interval instead of branching)
     const bool more = k + R < k_steps;
-    const uint32_t k_pre = more ? k + R : k_steps - 1;
-    double a_pre[NU][EPT];
-#pragma unroll
-    for (int j = 0; j < NU; ++j) ld_row<EPT>(io.a + ((k_pre * NU + j) * n32 + env0), a_pre[j]);
 
     // SP[t] (shown in the observation) and SP[t+1] (enters the reward)
     double spc[NSP][EPT], spn[NSP][EPT];
@@ -297,7 +354,7 @@ wsm_rollout_kernel(const __grid_constant__ pcg_desc d, const __grid_constant__ p
       }
     }
     const int c = k / R;
-    mbar_wait(&sp.full_x[s], c & 1);
+    mbar_wait_backoff(&sp.full_x[s], c & 1);
     // (written in the prologue before the tile's ring was released: ordered by the full_a -> full_x chain)
     const uchar2 d0 = sh.done0[p][lane];
     const bool done0[EPT] = {d0.x != 0, d0.y != 0};
@@ -360,10 +417,11 @@ wsm_rollout_kernel(const __grid_constant__ pcg_desc d, const __grid_constant__ p
     st_flags<EPT>(io.done + row, done);
     st_flags<EPT>(io.violated + row, violated);
 
-    if (more) {                                                                // hand interval k + R to the integrator
+    if (more) {                               // interval k + R: global -> ring slot s, arrival when the bytes have landed
 #pragma unroll
-      for (int j = 0; j < NU; ++j) sp.a[s][j][lane] = make_double2(a_pre[j][0], a_pre[j][1]);
-      mbar_arrive(&sp.full_a[s]);
+      for (int j = 0; j < NU; ++j)
+        cp_async16(&sp.a[s][j][lane], io.a + ((static_cast<uint32_t>(k + R) * NU + j) * n32 + env0));
+      cp_async_arrive(&sp.full_a[s]);
     }
     if (k == k_steps - 1 && io.done_state) {                                   // the sticky flag after this launch
 #pragma unroll

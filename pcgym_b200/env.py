@@ -218,6 +218,7 @@ class make_env:
 
         # pcgym.py:113-125 (after the model so the affine probe knows the dimensions)
         self.constraint_active = False
+        self._host_constraints = False
         self.r_penalty = False
         self.info = {}
         self.n_con = 0
@@ -226,10 +227,18 @@ class make_env:
             self.done_on_constraint = P["done_on_cons_vio"]
             self.r_penalty = P["r_penalty"]
             self.constraint_active = True
-            self._G, self._h = self._affine_constraints()
-            self.n_con = self._h.shape[0]
-            if self.n_con > nat.MAX_NCON:
-                raise ValueError(f"at most {nat.MAX_NCON} constraints are supported")
+            # A callable that is not affine in (state, uk) cannot be fused: it then runs UNFUSED in step() on the
+            # tensors the kernel returns (like a Python custom_reward), and rollout() refuses it.
+            self._host_constraints = False
+            try:
+                self._G, self._h = self._affine_constraints()
+                self.n_con = self._h.shape[0]
+                if self.n_con > nat.MAX_NCON:
+                    raise ValueError(f"at most {nat.MAX_NCON} constraints are supported")
+            except NotImplementedError:
+                self._host_constraints = True
+                probe = np.asarray(self.constraints(np.ones(self._n_obs), np.ones(self.Nu)), dtype=np.float64)
+                self.n_con = int(probe.reshape(-1).shape[0])                       # pcgym.py:124
 
         self._host_tables()
         self._desc = self._build_desc()
@@ -376,8 +385,9 @@ class make_env:
         self._host_reward = self.custom_reward and self._ocp is None      # Python callable: unfused path
         flags |= nat.F_NORMALISE_O if (self.normalise_o is True and not self._host_reward) else 0
         flags |= nat.F_A_DELTA if (self.a_delta and self.normalise_a) else 0
-        flags |= nat.F_R_PENALTY if self.r_penalty else 0
-        flags |= nat.F_DONE_ON_VIOLATION if (self.constraint_active and self.done_on_constraint) else 0
+        fused_con = self.constraint_active and not self._host_constraints
+        flags |= nat.F_R_PENALTY if (self.r_penalty and fused_con) else 0
+        flags |= nat.F_DONE_ON_VIOLATION if (fused_con and self.done_on_constraint) else 0
         flags |= nat.F_ADAPTIVE if self.integrator["adaptive"] else 0
         flags |= nat.F_SP_HIDDEN if self._sp_hidden else 0
         d.flags = flags
@@ -461,8 +471,8 @@ class make_env:
                     w = float(r_scale.get(s, 1))
                     d.batch_w[names.index(s)] += w if self.maximise_reward else -w
 
-        d.n_con = self.n_con
-        if self.constraint_active:
+        d.n_con = self.n_con if fused_con else 0
+        if fused_con:
             G, h = self._G.copy(), self._h.copy()
             n_s = self._n_obs
             if P.get("constraint_units", "reference") == "reference":
@@ -516,7 +526,7 @@ class make_env:
         self._h_carry = z(n)
         self._n_rhs = z(n, dtype=torch.int32)
         # cons_info lives as [N, n_con, n_envs] so the kernel writes rows in place; exposed as (n_con, N, n_envs)
-        self._cons = z(self.N, max(self.n_con, 1), n) if self.n_con else None
+        self._cons = z(self.N, max(self.n_con, 1), n) if self.n_con else None      # (host constraints write it from step())
         self._theta = None
         if self._per_env_theta:                      # [nparam, n]: defaults, then the user's per-env rows
             base = torch.tensor([float(v) for v in self.model.info()["parameters"].values()], dtype=f64, device=dev)
@@ -543,6 +553,7 @@ class make_env:
                  "violated": torch.empty(K, n, dtype=torch.uint8, device=dev),
                  "x": torch.empty(K, self.Nx_oracle, n, dtype=f64, device=dev) if want_x else None}
             if len(self._bufs) > 4:
+                self.host_sync()             # nothing cached may still be the source / target of a copy in flight
                 self._bufs.clear()
             self._bufs[key] = b
         return b
@@ -562,7 +573,7 @@ class make_env:
         io.z, io.tail = p(z), p(self._tail)
         io.x_traj, io.obs, io.reward = p(bufs["x"]), p(bufs["obs"]), p(bufs["reward"])
         io.done, io.violated = p(bufs["done"]), p(bufs["violated"])
-        if self._cons is not None:
+        if self._cons is not None and not self._host_constraints:
             io.g0 = p(self._cons[0])
             io.g = self._cons[self.t + 1].data_ptr() if self.t + 1 < self.N else None
         io.done_state, io.status, io.h_carry, io.n_rhs = p(self._done_state), p(self._status), p(self._h_carry), p(self._n_rhs)
@@ -670,12 +681,26 @@ class make_env:
         if z is not None:                                    # externally supplied N(0,1) draws, [n_envs, nx]
             z = torch.as_tensor(np.asarray(z, dtype=np.float64)) if not isinstance(z, torch.Tensor) else z
             z = z.to(device=self.device, dtype=torch.float64).reshape(n, self.Nx_oracle).T.contiguous()[None]
-        a_save_old = self._a_save.clone() if (self._host_reward and self.a_delta) else None
+        a_save_old = self._a_save.clone() if ((self._host_reward or self._host_constraints) and self.a_delta) else None
         t_old = self.t
+        if self._host_constraints and t_old == 0:                                  # pcgym.py:416-420 (result discarded)
+            self._constraint_check_host(self._uk_pre(self._a_step[0], a_save_old), numpy_in)
         out = self._launch(self._a_step, 1, want_x=False, z=z, desc=self._desc_step)
         obs_soa, r, done, violated = out["obs"][0], out["reward"][0], out["done"][0], out["violated"][0]
-        if self._copy_outputs or self._host_reward:
+        if self._copy_outputs or self._host_reward or self._host_constraints:
             obs_soa, r = obs_soa.clone(), r.clone()
+        if self._host_constraints:                                                 # pcgym.py:444-446, 556-557, 529-530
+            violated = self._constraint_check_host(self._uk(self._a_step[0], a_save_old, t_old), numpy_in).view(torch.uint8)
+            vb = violated.view(torch.bool)
+            if self.done_on_constraint:
+                done = done.clone()
+                done |= violated
+                self._done_state |= violated
+            if self.r_penalty and not self._host_reward:
+                if self.reward == "SP_reward_fn":
+                    r = r - 1000.0 * len(self._sp_keys) * vb                        # once per SP key
+                elif self.t == self.N - 1:
+                    r = r - 1000.0 * vb
         if self._host_reward:
             r, obs_soa = self._custom_reward(obs_soa, self._a_step[0], a_save_old, t_old, violated.view(torch.bool), numpy_in)
         elif self._obs_mask_bits:
@@ -719,6 +744,35 @@ class make_env:
                 rows.append(v[None])
         return torch.cat(rows, dim=0)
 
+    def _uk_pre(self, a_soa, a_save_old):
+        """uk as the t == 0 pre-check sees it (pcgym.py:416-420): this interval's input, disturbances of t + 1."""
+        return self._uk(a_soa, a_save_old, 0)
+
+    def _constraint_check_host(self, uk, numpy_in):
+        """constraint_check / con_checker (pcgym.py:560-615) for a callable that could not be fused: evaluated on the
+        physical state vector and uk -- after the reference's un-normalisation of already-physical values when
+        constraint_units == "reference" (pcgym.py:597-608).  n_envs == 1: numpy vectors like the reference;
+        batched: numpy arrays [Nx, n] and [Nu, n] (state-major, so g written for one env -- x[1], u[0] -- vectorises
+        as is) returning [n_con, n].  Writes cons_info[:, t, :], returns violated [n] (bool tensor)."""
+        st = self.state
+        st = st.T if isinstance(st, torch.Tensor) else torch.as_tensor(st, device=self.device)[:, None]     # [Nx, n]
+        st, uk = st.detach().cpu().numpy().astype(np.float64), uk.detach().cpu().numpy().astype(np.float64)
+        if self.env_params.get("constraint_units", "reference") == "reference":
+            if self.normalise_a is True:
+                lo, hi = self._a_lo[:, None], self._a_hi[:, None]
+                uk = (uk + 1) * (hi - lo) / 2 + lo
+            if self.normalise_o is True:
+                lo = self.observation_space_base.low.astype(np.float64)[:, None]
+                hi = self.observation_space_base.high.astype(np.float64)[:, None]
+                st = (st + 1) * (hi - lo) / 2 + lo
+        if self.n_envs == 1:
+            g = np.asarray(self.constraints(st[:, 0], uk[:, 0]), dtype=np.float64).reshape(self.n_con, 1)
+        else:
+            g = np.asarray(self.constraints(st, uk), dtype=np.float64).reshape(self.n_con, self.n_envs)
+        gd = torch.from_numpy(g).to(self.device)
+        self._cons[self.t] = gd
+        return (gd > 0).any(dim=0)
+
     def _custom_reward(self, obs_phys, a_soa, a_save_old, t_old, violated, numpy_in):
         """Python-callable custom reward (pcgym.py:470-471): `f(env, obs, uk, violated)` with the NOISY
         physical observation.  A callable cannot be fused, so the kernel ran with reward NONE and emitted
@@ -741,9 +795,12 @@ class make_env:
         return r, obs
 
     # ------------------------------------------------------------------ rollout: K intervals, one launch
-    def rollout(self, actions, z=None, want_x=True):
+    def rollout(self, actions, z=None, want_x=True, copy=False):
         """actions: [K, nu_a, n_envs] (struct-of-arrays, preferred) or [K, n_envs, nu_a]; device or host tensor.
-        Returns SoA tensors: obs [K, Nx, n], reward [K, n], done/violated [K, n] (uint8), x [K, nx, n]."""
+        Returns SoA tensors: obs [K, Nx, n], reward [K, n], done/violated [K, n] (uint8), x [K, nx, n].
+        The returned tensors are the env's own output buffers for this (K, want_x): the next rollout() /
+        rollout_host() of the same shape OVERWRITES them (no allocation on the hot path).  Pass copy=True (or clone
+        what you keep) to own the result."""
         if not self._dev_ready:
             raise RuntimeError("call reset() before rollout()")
         self._join_pipe()
@@ -759,6 +816,9 @@ class make_env:
         if self._host_reward:
             raise NotImplementedError("rollout() needs a fused reward: use SP / batch reward or custom_reward="
                                       "{'kind': 'ocp_tracking', ...}; Python-callable rewards work through step()")
+        if self._host_constraints:
+            raise NotImplementedError("rollout() needs fusable (affine or box) constraints; a non-affine callable is "
+                                      "evaluated unfused through step()")
         a = a.to(device=self.device, dtype=torch.float64, non_blocking=True).contiguous()
         K = a.shape[0]
         if self.t + K > self.N - 1:
@@ -767,22 +827,36 @@ class make_env:
             z = z.to(device=self.device, dtype=torch.float64).contiguous()
             if z.shape != (K, self.Nx_oracle, n):
                 raise ValueError(f"z must be [K, {self.Nx_oracle}, {n}]")
-        return self._launch(a, K, want_x=want_x, z=z)
+        out = self._launch(a, K, want_x=want_x, z=z)
+        return {k: (v.clone() if v is not None else None) for k, v in out.items()} if copy else out
 
-    def rollout_host(self, actions, out=None, chunks: int = 8, want_x: bool = False, wait: bool = True):
+    HOST_OUTPUTS = ("obs", "reward", "done", "violated", "x", "obs_last", "return")
+
+    def rollout_host(self, actions, out=None, chunks: int = 8, want_x: bool = False, wait: bool = True, outputs=None):
         """`rollout` for HOST buffers: `actions` [K, nu_a, n_envs] float64 in (ideally pinned) host memory; returns
-        pinned host tensors obs [K, Nx, n], reward [K, n], done [K, n] (and x [K, nx, n] if `want_x`), reusing `out`
-        when given.  The K intervals are cut into `chunks` time slices -- contiguous in both the action and the
-        output layouts -- and pipelined over three streams: the host->device copy of slice c+1 and the
-        device->host copy of slice c-1 overlap the kernel of slice c (PCIe is full duplex), so the call costs about
-        max(H2D, D2H) instead of their sum.  The result is complete when the call returns (it synchronises).
-        With `wait=False` the call only enqueues: successive calls then overlap as well (slice j of the next call waits
-        for the device->host copy of slice j of this one, nothing more), and `host_sync()` must be called before `out`
-        is read -- alternate two `out` sets to keep one readable."""
+        pinned host tensors, reusing `out` when given.  `outputs` names what is brought back (default
+        ("obs", "reward", "done"), plus "x" with `want_x`):
+            per interval   "obs" [K, Nx, n]  "reward" [K, n]  "done" [K, n]  "violated" [K, n]  "x" [K, nx, n]
+            reduced        "obs_last" [Nx, n] (observation after the last interval)   "return" [n] (sum of the K rewards,
+                           reduced on the device)
+        A consumer that needs the returns and the final observation of an episode moves 32 B per env instead of
+        3.3 KB.  The K intervals are cut into `chunks` time slices -- contiguous in both the action and the output
+        layouts -- and pipelined over three streams: the host->device copy of slice c+1 and the device->host copy of
+        slice c-1 overlap the kernel of slice c (PCIe is full duplex), so the call costs about max(H2D, D2H) instead
+        of their sum.  The result is complete when the call returns (it synchronises).  With `wait=False` the call
+        only enqueues: successive calls then overlap as well (slice j of the next call waits for the device->host
+        copy of slice j of this one, nothing more), and `host_sync()` must be called before `out` is read --
+        alternate two `out` sets to keep one readable."""
         if not self._dev_ready:
             raise RuntimeError("call reset() before rollout_host()")
-        if self._host_reward:
-            raise NotImplementedError("rollout_host() needs a fused reward (see rollout())")
+        if self._host_reward or self._host_constraints:
+            raise NotImplementedError("rollout_host() needs a fused reward and fusable constraints (see rollout())")
+        if outputs is None:
+            outputs = ("obs", "reward", "done") + (("x",) if want_x else ())
+        outputs = tuple(outputs)
+        bad = [k for k in outputs if k not in self.HOST_OUTPUTS]
+        if bad:
+            raise ValueError(f"unknown outputs {bad}; choose from {self.HOST_OUTPUTS}")
         n, nu_a = self.n_envs, self._a_lo.shape[0]
         a = actions if isinstance(actions, torch.Tensor) else torch.as_tensor(np.asarray(actions, dtype=np.float64))
         if a.device.type != "cpu" or a.dtype != torch.float64 or a.ndim != 3 or a.shape[1:] != (nu_a, n):
@@ -793,11 +867,16 @@ class make_env:
             raise IndexError(f"rollout of {K} steps from t = {self.t} exceeds the episode (N - 1 = {self.N - 1} steps)")
         if self._desc.noise == nat.NOISE["external"]:
             raise ValueError("noise_mode='external' is not supported by rollout_host()")
+        want_x = want_x or "x" in outputs
         dev = self.device
-        keys = ("obs", "reward", "done") + (("x",) if want_x else ())
+        keys = tuple(k for k in outputs if k in ("obs", "reward", "done", "violated", "x"))
         bufs = self._out_bufs(K, want_x)
         if out is None:
             out = {k: torch.empty(bufs[k].shape, dtype=bufs[k].dtype).pin_memory() for k in keys}
+            if "obs_last" in outputs:
+                out["obs_last"] = torch.empty(bufs["obs"].shape[1:], dtype=torch.float64).pin_memory()
+            if "return" in outputs:
+                out["return"] = torch.empty(n, dtype=torch.float64).pin_memory()
         if self._pipe is None:
             self._pipe = (torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev))
         s_in, s_out = self._pipe
@@ -806,12 +885,14 @@ class make_env:
         if a_dev is None:
             a_dev = self._bufs[("a_dev", K)] = torch.empty(K, nu_a, n, dtype=torch.float64, device=dev)
         edges = [int(e) for e in np.linspace(0, K, max(1, min(int(chunks), K)) + 1).astype(int)]
-        prev = self._pipe_prev if self._pipe_prev is not None and self._pipe_prev[0] == (K, tuple(edges), want_x) else None
+        sig = (K, tuple(edges), want_x, outputs)
+        prev = self._pipe_prev if self._pipe_prev is not None and self._pipe_prev[0] == sig else None
         if prev is None:                          # different slicing (or first call): order behind everything in flight
             main.wait_stream(s_out)
             s_in.wait_stream(main)
             s_out.wait_stream(main)
         ev_ks, ev_outs = [], []
+        last = len(edges) - 2
         for j, (k0, k1) in enumerate(zip(edges[:-1], edges[1:])):
             with torch.cuda.stream(s_in):
                 if prev is not None:
@@ -823,17 +904,28 @@ class make_env:
             if prev is not None:
                 main.wait_event(prev[2][j])       # ... and its results have left this output slice
             self._launch(a_dev[k0:k1], k1 - k0, want_x, bufs={k: (v[k0:k1] if v is not None else None) for k, v in bufs.items()})
+            ret_dev = None
+            if j == last and "return" in outputs:
+                ret_dev = self._bufs.get(("ret", K))
+                if ret_dev is None:
+                    ret_dev = self._bufs[("ret", K)] = torch.empty(n, dtype=torch.float64, device=dev)
+                torch.sum(bufs["reward"], dim=0, out=ret_dev)
             ev_k = torch.cuda.Event()
             ev_k.record(main)
             with torch.cuda.stream(s_out):
                 s_out.wait_event(ev_k)
                 for k in keys:
                     out[k][k0:k1].copy_(bufs[k][k0:k1], non_blocking=True)
+                if j == last:
+                    if "obs_last" in outputs:
+                        out["obs_last"].copy_(bufs["obs"][K - 1], non_blocking=True)
+                    if ret_dev is not None:
+                        out["return"].copy_(ret_dev, non_blocking=True)
                 ev_o = torch.cuda.Event()
                 ev_o.record(s_out)
             ev_ks.append(ev_k)
             ev_outs.append(ev_o)
-        self._pipe_prev = ((K, tuple(edges), want_x), ev_ks, ev_outs)
+        self._pipe_prev = (sig, ev_ks, ev_outs)
         if wait:
             self.host_sync()
         return out

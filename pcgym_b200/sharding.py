@@ -62,25 +62,51 @@ def init_from_env(backend: str | None = None):
     return rank, world, local
 
 
-def bind_to_gpu_numa(local_rank: int) -> list:
-    """Pin this process to the CPUs NVML reports as closest to GPU `local_rank` (its NUMA node), so that pinned
-    host buffers allocated afterwards are first-touched next to the GPU's PCIe root.  With one process per GPU and
-    host<->device copies in the timed region (bench.py `e2e`) this keeps the ranks from sharing one socket's memory
-    controllers.  Returns the CPU list it bound to ([] = left unchanged: NVML unavailable or mask empty)."""
+def bind_to_gpu_numa(local_rank: int, local_world: int = 1) -> list:
+    """Pin this process to CPUs close to GPU `local_rank` (NVML's affinity mask = its NUMA node), so that pinned host
+    buffers allocated afterwards are first-touched next to the GPU's PCIe root.  When several local GPUs report the
+    SAME mask (one socket serving all of them) the mask is cut into disjoint, contiguous slices, one per rank, so the
+    ranks' Python launch threads never time-share a core (round 1 pinned all 8 ranks onto the same 32 CPUs).
+    Returns the CPU list it bound to ([] = left unchanged: NVML unavailable or mask empty)."""
     try:
         import pynvml
         pynvml.nvmlInit()
-        h = pynvml.nvmlDeviceGetHandleByIndex(int(local_rank))
         n_words = (os.cpu_count() + 63) // 64
-        mask = pynvml.nvmlDeviceGetCpuAffinity(h, n_words)
-        cpus = [64 * w + b for w, word in enumerate(mask) for b in range(64) if (int(word) >> b) & 1]
         allowed = os.sched_getaffinity(0)
-        cpus = [c for c in cpus if c in allowed]
-        if cpus:
-            os.sched_setaffinity(0, cpus)
+
+        def mask_of(g):
+            m = pynvml.nvmlDeviceGetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(int(g)), n_words)
+            return tuple(c for c in (64 * w + b for w, word in enumerate(m) for b in range(64) if (int(word) >> b) & 1)
+                         if c in allowed)
+
+        mine = mask_of(local_rank)
+        if not mine:
+            return []
+        peers = [g for g in range(max(int(local_world), 1)) if mask_of(g) == mine]
+        cpus = slice_cpus(list(mine), peers.index(local_rank) if local_rank in peers else 0, max(len(peers), 1))
+        os.sched_setaffinity(0, cpus)
         return cpus
     except Exception:
         return []
+
+
+def slice_cpus(cpus: list, i: int, m: int) -> list:
+    """Slice i of m of a CPU list: contiguous, disjoint, at least one CPU each (falls back to sharing when m > len)."""
+    if m <= 1 or len(cpus) < m:
+        return list(cpus)
+    lo, hi = (i * len(cpus)) // m, ((i + 1) * len(cpus)) // m
+    return list(cpus[lo:hi])
+
+
+def gather_over_ranks(values, device=None) -> list:
+    """[[v0, v1, ...] of rank 0, of rank 1, ...]: small per-rank diagnostics (kernel time, enqueue time) for rank 0."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return [[float(v) for v in values]]
+    t = torch.tensor([float(v) for v in values], dtype=torch.float64,
+                     device=device or ("cuda" if dist.get_backend() == "nccl" else "cpu"))
+    outs = [torch.zeros_like(t) for _ in range(dist.get_world_size())]
+    dist.all_gather(outs, t)
+    return [[float(v) for v in o.tolist()] for o in outs]
 
 
 def max_over_ranks(value: float, device=None) -> float:

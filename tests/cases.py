@@ -156,6 +156,52 @@ def crystallization():
     }
 
 
+def four_tank_ocp():
+    """pc-gym_paper/train_policies/four_tank/4tank_train.py:54-85 as written: two setpoints, 5 % noise and the
+    script's own `oracle_reward` (:16-52, the OCP tracking reward with R = 0.1) as custom_reward.  BASELINE config 5's
+    four_tank shard.  (N = 60, tsim = 1000 in the script; 24 intervals of the same dt here to keep the fixture small.)"""
+    N = 24
+    SP = {"h3": [0.5] * (N // 2) + [0.1] * (N // 2), "h4": [0.2] * (N // 2) + [0.3] * (N // 2)}
+    return {
+        "N": N, "tsim": N * 1000 / 60, "SP": SP,
+        "o_space": {"low": np.array([0.0] * 6), "high": np.array([0.6] * 6)},
+        "a_space": {"low": np.array([0.1, 0.1]), "high": np.array([10.0, 10.0])},
+        "x0": np.array([0.141, 0.112, 0.072, 0.42, SP["h3"][0], SP["h4"][0]]),
+        "model": "four_tank", "normalise_a": True, "normalise_o": True,
+        "noise": True, "noise_percentage": 0.05,
+        "custom_reward": ocp_reward(0.1),
+    }
+
+
+def cryst_reward(R=0.01):
+    """The crystallization script's reward (pc-gym_paper/train_policies/crystalisation/cryst_train.py:17-48, written
+    independently): CV and Ln are DERIVED from the noisy moments, normalised with o_space[5:7], tracked against
+    SP['CV'][t], SP['Ln'][t]; plus R * (change of the a_space-normalised input)^2."""
+    def reward(env, x, u, violated):
+        P = env.env_params
+        lo, hi = np.asarray(P["o_space"]["low"], float)[[5, 6]], np.asarray(P["o_space"]["high"], float)[[5, 6]]
+        a_lo, a_hi = np.asarray(P["a_space"]["low"], float), np.asarray(P["a_space"]["high"], float)
+        u = np.asarray(u, float)
+        if not hasattr(env, "u_prev"):
+            env.u_prev = u
+        cv = (x[2] * x[0] / x[1] ** 2 - 1) ** 0.5
+        ln = x[1] / x[0]
+        e_cv = (P["SP"]["CV"][env.t] - cv) / (hi[0] - lo[0])
+        e_ln = (P["SP"]["Ln"][env.t] - ln) / (hi[1] - lo[1])
+        un, up = (u - a_lo) / (a_hi - a_lo), (env.u_prev - a_lo) / (a_hi - a_lo)
+        env.u_prev = u
+        return -float(e_cv ** 2 + e_ln ** 2 + np.sum(R * (un - up) ** 2))
+    return reward
+
+
+def cryst_ocp():
+    """cryst_train.py:51-100 as written: a_delta mode, two setpoints AND the script's own reward.  BASELINE config 5's
+    crystallization shard."""
+    p = crystallization()
+    p["custom_reward"] = cryst_reward(0.01)
+    return p
+
+
 def extraction():
     """pc-gym_paper/train_policies/multistage_extraction/me_train.py:54-93 with an X0 disturbance."""
     N = 20
@@ -192,6 +238,8 @@ CASES = {
     "cstr_one_dist": cstr_one_dist,
     "cstr_batch_reward": cstr_batch_reward,
     "cstr_ocp": cstr_ocp,
+    "four_tank_ocp": four_tank_ocp,
+    "cryst_ocp": cryst_ocp,
     "first_order": first_order,
     "four_tank": four_tank,
     "crystallization": crystallization,

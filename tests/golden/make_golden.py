@@ -181,13 +181,30 @@ def gen_traj(outdir):
         print("wrote traj", name, x.shape, u.shape, dt)
 
 
+def _script_function(path, name):
+    """One function definition lifted out of a reference SCRIPT (the training scripts run SB3 on import, so they cannot
+    be imported): the reference's own source text of `name`, compiled as is."""
+    import ast
+    src = open(path).read()
+    node = next(n for n in ast.parse(src).body if isinstance(n, ast.FunctionDef) and n.name == name)
+    ns = {"np": np}
+    exec(compile(ast.Module(body=[node], type_ignores=[]), path, "exec"), ns)
+    return ns[name]
+
+
 # ---------------------------------------------------------------- step fixtures ----
-def gen_steps(make_env, outdir):
+def gen_steps(make_env, outdir, only=None):
     for name, factory in cases.CASES.items():
+        if only and name not in only:
+            continue
         params = factory()
         if name == "cstr_ocp":      # pin the fused / restated reward against the reference's own function
             ref = _load("ref_custom_reward", f"{REF}/pc-gym_paper/train_policies/cstr/custom_reward.py")
             params["custom_reward"] = ref.sp_track_reward
+        if name == "four_tank_ocp":
+            params["custom_reward"] = _script_function(f"{REF}/pc-gym_paper/train_policies/four_tank/4tank_train.py", "oracle_reward")
+        if name == "cryst_ocp":
+            params["custom_reward"] = _script_function(f"{REF}/pc-gym_paper/train_policies/crystalisation/cryst_train.py", "oracle_reward")
         acts = cases.actions_for(name, params)
         env = make_env(params)
         draws = []
@@ -267,7 +284,11 @@ def gen_kat(make_env, outdir):
 
 if __name__ == "__main__":
     mc, make_env = load_reference()
-    gen_rhs(mc, f"{HERE}/rhs_vectors.npz")
-    gen_traj(HERE)
-    gen_steps(make_env, HERE)
-    gen_kat(make_env, HERE)
+    only = sys.argv[1:]                   # e.g. `make_golden.py four_tank_ocp cryst_ocp`: just these step fixtures
+    if only:
+        gen_steps(make_env, HERE, only)
+    else:
+        gen_rhs(mc, f"{HERE}/rhs_vectors.npz")
+        gen_traj(HERE)
+        gen_steps(make_env, HERE)
+        gen_kat(make_env, HERE)

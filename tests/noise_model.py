@@ -41,7 +41,7 @@ def load_table():
         ln = ln.strip()
         if ln and not ln.startswith("//"):
             rows.append([float.fromhex(v) for v in ln.rstrip(",").split(",")])
-    return np.array(rows)                                  # [256, 8]
+    return np.array(rows)                                  # [512, 6]
 
 
 def icdf_table_eval(w, tab=None):
@@ -53,12 +53,12 @@ def icdf_table_eval(w, tab=None):
     m = wp * np.uint64(2) + np.uint64(1)
     b = np.floor(np.log2(m.astype(np.float64))).astype(np.int64)          # leading-one index (m < 2^32: exact in fp64)
     mn = (m << (31 - b).astype(np.uint64)) & MASK
-    idx = b * 8 + ((mn >> np.uint64(28)) & np.uint64(7)).astype(np.int64)
-    v = (((mn << np.uint64(4)) & MASK) ^ np.uint64(0x80000000)).astype(np.int64)
+    idx = b * 16 + ((mn >> np.uint64(27)) & np.uint64(15)).astype(np.int64)
+    v = (((mn << np.uint64(5)) & MASK) ^ np.uint64(0x80000000)).astype(np.int64)
     v = np.where(v >= (1 << 31), v - (1 << 32), v).astype(np.float64)     # as signed 32-bit
     c = tab[idx]
-    z = c[:, 7]
-    for k in range(6, -1, -1):
+    z = c[:, 5]
+    for k in range(4, -1, -1):
         z = z * v + c[:, k]
     return np.where(flip, -z, z)
 
