@@ -83,6 +83,85 @@ def cstr_headline(n_envs=N_ENVS, device="cuda", seed=0, env_id0=0):
     return params, (acts.to(device) if device != "cpu" else acts)
 
 
+# BASELINE config 5: 524 288 envs over 8 GPUs = 65 536 per GPU, a third each of three models, every GPU the same mix.
+# Even part sizes keep every row access 128-bit (two envs per thread where the kernel family has that form).
+CONFIG5_PER_GPU = {"cstr": 21846, "four_tank": 21846, "crystallization": 21844}
+# integrator per part: fixed Tsit5 substeps that keep the trajectories within the north-star rtol 1e-6 of the converged
+# solution for these definitions (asserted by tests/test_gpu_mixed.py::test_config5_parts_against_the_oracle_env)
+CONFIG5_INTEGRATOR = {"cstr": {"scheme": "tsit5", "adaptive": False, "n_sub": 2},
+                      "four_tank": {"scheme": "tsit5", "adaptive": False, "n_sub": 2},
+                      "crystallization": {"scheme": "tsit5", "adaptive": False, "n_sub": 8}}
+
+
+def config5_parts(per_gpu=None, device="cuda", seed=0, rank=0):
+    """(parts, actions) of BASELINE config 5 for ONE rank: name -> env_params / [K, nu, n] actions.
+      cstr             the headline CSTR plus live disturbances Ti ~ U(340, 352) held for four intervals and
+                       Caf ~ U(0.9, 1.1), PER ENV and per step (bounds as docs/guides/disturbances.md).  SURVEY 8(d)
+                       writes U(340, 360); with a feed hotter than ~354 K about 1 % of the envs IGNITE (thermal runaway to
+                       > 420 K, stiffness ratio ~1e4 -- the reference's CVODES follows it, no explicit pair does at this
+                       interval, and the kernel flags those envs in `status`).  A benchmark over flagged envs would time
+                       garbage, so the band stops below the ignition limit (measured with the oracle: 0 of 65 536 envs).
+      four_tank        pc-gym_paper/train_policies/four_tank/4tank_train.py:54-85 (N = 60, tsim = 1000, two setpoints,
+                       5 % noise, the script's OCP reward in its fused form); actions U(-0.5, 1): with the pumps held near
+                       their minimum for several intervals a tank runs dry and sqrt(h) is NaN, in the reference too
+      crystallization  pc-gym_paper/train_policies/crystalisation/cryst_train.py:51-100 (N = 30, a_delta from a_0 = 39,
+                       two setpoints, 0.1 % noise, the script's CV / Ln reward in its fused form)
+    Env ids are offset by rank so a sharded run draws the noise of the single-process run."""
+    import torch
+    per_gpu = dict(per_gpu or CONFIG5_PER_GPU)
+    rng = np.random.default_rng(seed + 1000 * rank)
+    g = torch.Generator(device="cpu").manual_seed(seed + 7919 * rank)
+    parts, acts = {}, {}
+
+    n = per_gpu["cstr"]
+    p, a = cstr_headline(n_envs=n, device=device, seed=seed, env_id0=rank * n)
+    N = p["N"]
+    p["disturbances"] = {"Ti": np.repeat(rng.uniform(340, 352, (n, (N + 3) // 4)), 4, axis=1)[:, :N],
+                         "Caf": rng.uniform(0.9, 1.1, (n, N))}
+    p["disturbance_bounds"] = {"low": np.array([330.0, 0.8]), "high": np.array([370.0, 1.2])}
+    p["o_space"] = {"low": np.array([0.7, 300.0, 0.8]), "high": np.array([1.0, 350.0, 0.9])}
+    p["integrator"] = dict(CONFIG5_INTEGRATOR["cstr"])
+    parts["cstr"], acts["cstr"] = p, a
+
+    n, N = per_gpu["four_tank"], 60
+    SP = {"h3": [0.5] * (N // 2) + [0.1] * (N // 2), "h4": [0.2] * (N // 2) + [0.3] * (N // 2)}
+    parts["four_tank"] = {
+        "model": "four_tank", "N": N, "tsim": 1000, "SP": SP, "n_envs": n, "device": device,
+        "o_space": {"low": np.array([0.0] * 6), "high": np.array([0.6] * 6)},
+        "a_space": {"low": np.array([0.1, 0.1]), "high": np.array([10.0, 10.0])},
+        "x0": np.array([0.141, 0.112, 0.072, 0.42, SP["h3"][0], SP["h4"][0]]),
+        "normalise_a": True, "normalise_o": True, "noise": True, "noise_percentage": 0.05,
+        "custom_reward": {"kind": "ocp_tracking", "R": 0.1},
+        "integrator": dict(CONFIG5_INTEGRATOR["four_tank"]), "seed": seed, "env_id0": rank * n,
+    }
+    acts["four_tank"] = (torch.rand(N - 1, 2, n, generator=g, dtype=torch.float64) * 1.5 - 0.5).to(device)
+
+    n, N = per_gpu["crystallization"], 30
+    mu = [1478.00986666666, 22995.8230590611, 1800863.24079725, 248516167.940593]
+    parts["crystallization"] = {
+        "model": "crystallization", "N": N, "tsim": 30, "SP": {"CV": [1] * N, "Ln": [15] * N}, "n_envs": n,
+        "device": device,
+        "o_space": {"low": np.array([0, 0, 0, 0, 0, 0, 0, 0.9, 14.0]),
+                    "high": np.array([1e20, 1e20, 1e20, 1e20, 0.5, 2, 20, 1.1, 16])},
+        "a_space": {"low": np.array([-1.0]), "high": np.array([1.0])},
+        "x0": np.array(mu + [0.15861523304, np.sqrt(mu[2] * mu[0] / mu[1] ** 2 - 1), mu[1] / (mu[0] + 1e-6), 1, 15]),
+        "normalise_a": True, "normalise_o": True, "noise": True, "noise_percentage": 0.001,
+        "a_0": 39, "a_delta": True, "a_space_act": {"low": np.array([10.0]), "high": np.array([40.0])},
+        "custom_reward": {"kind": "cryst_tracking", "R": 0.01},
+        "integrator": dict(CONFIG5_INTEGRATOR["crystallization"]), "seed": seed, "env_id0": rank * n,
+    }
+    acts["crystallization"] = (torch.rand(N - 1, 1, n, generator=g, dtype=torch.float64) * 2 - 1).to(device)
+    return parts, acts
+
+
+def config5_bytes_per_env_step(env):
+    """Algorithmic rollout bytes of one env-step of a part: actions + per-env disturbance rows read, x / obs / reward
+    (+ cons_info) written, two flag bytes (shared setpoint schedule)."""
+    nx, nu = env.Nx_oracle, env._a_lo.shape[0]
+    nd = len(env._d_keys) if (env.disturbance_active and getattr(env, "_d_per_env", False)) else 0
+    return 8 * (nu + nd) + 8 * (nx + env._n_obs + 1 + env.n_con) + 2
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled every 100 ms while the GPU is under the benchmark's load
     (B200_PROFILING.md).  Rank 0 only, started >= 2 s before the timed region (NVML initialisation enumerates every
@@ -188,6 +267,159 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+# ------------------------------------------------------------------------------------------ config 5 (mixed batch)
+def run_config5(args):
+    """`--config 5`: the mixed CSTR(+disturbances) / four_tank / crystallization population, 65 536 envs per GPU,
+    through pcgym_b200.MixedBatch (one call per pass, the three parts' kernels concurrent on three streams).  A pass =
+    every part put back to its reset() state (rewind(to_x0=True)) and rolled through its whole episode (99 / 59 / 29
+    intervals); `status` must stay 0 on every env.  Same timing scheme as the headline: K passes captured in one CUDA
+    graph, one timed replay, barrier + synchronize on both sides, max over ranks."""
+    import torch
+    import torch.distributed as dist
+    from pcgym_b200 import _native as nat
+    from pcgym_b200 import MixedBatch, sharding
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
+    torch.cuda.set_device(local)
+    dev = f"cuda:{local}"
+    if world > 1:
+        sharding.init_from_env("nccl")
+        sharding.bind_to_gpu_numa(local, local_world)
+    W, K = max(args.warmup, 3), args.steps
+    scale = args.n_envs / N_ENVS
+    per_gpu = {k: max(2, 2 * int(v * scale / 2)) for k, v in CONFIG5_PER_GPU.items()}
+    parts, acts = config5_parts(per_gpu, device=dev, rank=rank)
+    mb = MixedBatch(parts)
+    mb.reset()
+    horizons = {k: int(a.shape[0]) for k, a in acts.items()}
+    steps_per_pass = mb.env_steps(horizons)
+    bytes_per_pass = sum(config5_bytes_per_env_step(mb.envs[k]) * mb.envs[k].n_envs * horizons[k] for k in mb.names)
+    lib = nat.lib()
+
+    def one_pass():
+        mb.rewind(to_x0=True)
+        return mb.rollout(acts)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    kernels = {}
+    for k in mb.names:                                    # which kernel family each part runs on
+        mb.envs[k].rewind(to_x0=True)
+        mb.envs[k].rollout(acts[k])
+        kernels[k] = lib.pcg_last_kernel().decode()
+    for _ in range(W):
+        one_pass()
+    barrier()
+    side = torch.cuda.Stream(device=dev)
+    side.wait_stream(torch.cuda.current_stream(dev))
+    with torch.cuda.stream(side):
+        one_pass()
+    torch.cuda.current_stream(dev).wait_stream(side)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    l0 = lib.pcg_launch_count()
+    with torch.cuda.graph(graph):
+        for _ in range(K):
+            one_pass()
+    launches = lib.pcg_launch_count() - l0
+    t_a, t_b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local, enabled=(rank == 0)) as clk:
+        t_end = time.perf_counter() + 1.5
+        while time.perf_counter() < t_end:
+            graph.replay()
+        barrier()
+        c_lo = time.perf_counter() - 1.0
+        t_a.record()
+        graph.replay()
+        t_b.record()
+        barrier()
+        t_end = time.perf_counter() + 0.5
+        while time.perf_counter() < t_end:
+            graph.replay()
+        torch.cuda.synchronize()
+        c_hi = time.perf_counter()
+    total_ms_local = t_a.elapsed_time(t_b)
+    total_ms = sharding.max_over_ranks(total_ms_local, dev)
+    value = world * steps_per_pass * K / (total_ms * 1e-3)
+
+    # each part alone (eager, CUDA events): where the pass time goes
+    alone = {}
+    for k in mb.names:
+        e = mb.envs[k]
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            e.rewind(to_x0=True)
+            e.rollout(acts[k])
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 5
+        b = config5_bytes_per_env_step(e)
+        alone[k] = {"n_envs": e.n_envs, "intervals": horizons[k], "ms": ms, "env_steps_per_s": e.n_envs * horizons[k] / (ms * 1e-3),
+                    "bytes_per_env_step": b, "GBps": e.n_envs * horizons[k] * b / (ms * 1e-3) / 1e9,
+                    "integrator": parts[k]["integrator"], "kernel": kernels[k]}
+    bad = sharding.max_over_ranks(float(mb.status_nonzero()), dev)
+    if bad:
+        raise SystemExit(f"config 5: {int(bad)} envs with a non-zero integrator status on some rank")
+
+    # end to end: pinned host actions in, (return, final observation, done) of every env back, per pass
+    a_host = {k: a.cpu().pin_memory() for k, a in acts.items()}
+    outs = ("return", "obs_last", "done")
+
+    def e2e_pass(sets):
+        mb.rewind(to_x0=True)
+        return mb.rollout_host(a_host, out=sets, wait=False, outputs=outs)
+    sets = e2e_pass(None)
+    mb.host_sync()
+    barrier()
+    Ke = max(3, min(K, 10))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(Ke):
+        e2e_pass(sets)
+        mb.host_sync()
+    e1.record()
+    barrier()
+    e2e_ms = sharding.max_over_ranks(e0.elapsed_time(e1), dev) / Ke
+    h2d = sum(a.numel() * 8 for a in a_host.values())
+    d2h = sum(v.numel() * v.element_size() for part in sets.values() for v in part.values())
+    per_rank = sharding.gather_over_ranks([total_ms_local / K], dev)
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peak, peak_src = hbm_peak()
+    achieved = bytes_per_pass / (total_ms / K * 1e-3) / 1e9
+    line = {
+        "metric": "env-steps/s", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": "BASELINE config 5: mixed CSTR (per-env live Ti / Caf disturbances) / four_tank (4tank_train.py) / "
+                               "crystallization (cryst_train.py, a_delta) population, a third each, same mix on every GPU; one "
+                               "MixedBatch.rollout per pass, every pass from the reset() state, status == 0 asserted",
+                   "n_envs_per_gpu": mb.n_envs, "n_envs_total": world * mb.n_envs, "parts": per_gpu, "intervals": horizons,
+                   "timed_region": "one replay of a CUDA graph holding the K passes",
+                   "parallelism": f"each part sharded evenly over {world} GPUs, no collective"},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": None, "algorithmic_bytes": bytes_per_pass, "peak_source": peak_src,
+                     "note": "whole pass (three concurrent kernels); per-part numbers under `parts_alone`"},
+        "parts_alone": alone,
+        "e2e": {"value": world * steps_per_pass / (e2e_ms * 1e-3), "unit": "env-steps/s", "ms_per_step": e2e_ms,
+                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "outputs": list(outs)},
+        "gpu_launches": int(launches), "per_rank": {"columns": ["graph_ms_per_step"], "rows": per_rank},
+        "clocks": clk.summary(c_lo, c_hi),
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 # ------------------------------------------------------------------------------------------ our arm
 def main():
     ap = argparse.ArgumentParser()
@@ -208,6 +440,8 @@ def main():
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    if args.config == 5:
+        return run_config5(args)
     if args.config != 3:
         sys.argv = [os.path.join(ROOT, "tools", "bench_models.py"), "--config", str(args.config), "--steps", str(args.steps),
                     "--warmup", str(args.warmup)]

@@ -96,6 +96,11 @@ enum pcg_reward {
                             (pc-gym_paper/train_policies/cstr/custom_reward.py:3-39)          */
 };
 
+/* pcg_desc.ocp_mode bit: the crystallization script's reward (pc-gym_paper/train_policies/crystalisation/
+ * cryst_train.py:17-48): setpoint 0 tracks CV = sqrt(mu2 mu0 / mu1^2 - 1), setpoint 1 tracks Ln = mu1 / mu0, both
+ * computed from the NOISY observation of states 0..2 instead of reading the CV / Ln states */
+#define PCG_OCP_MOMENTS 4
+
 enum pcg_flags {
   PCG_F_NORMALISE_A = 1 << 0,   /* pcgym.py:372-375                                 */
   PCG_F_NORMALISE_O = 1 << 1,   /* pcgym.py:483-493                                 */
@@ -199,7 +204,8 @@ typedef struct pcg_desc {
   /* PCG_REWARD_OCP */
   double ocp_R;                    /* control-cost weight R */
   double ocp_inv_span[PCG_MAX_NSP];/* 1/(o_hi - o_lo) of each setpoint's state */
-  int32_t ocp_mode;                /* 0: R*u_norm^2   1: R*(u_norm - u_prev_norm)^2   2: as 1, io.u_prev not yet valid */
+  int32_t ocp_mode;                /* bits 0-1: 0 R*u_norm^2, 1 R*(u_norm - u_prev_norm)^2, 2 as 1 but io.u_prev not yet valid;
+                                      | PCG_OCP_MOMENTS: the two tracked quantities are derived from the noisy moments */
   int32_t _pad3;
 } pcg_desc;
 

@@ -40,6 +40,7 @@ MODEL_IDS = {
 SCHEMES = {"rk4": 0, "dopri5": 1, "rk45": 1, "tsit5": 2}
 NOISE = {"off": 0, "philox": 1, "external": 2, "philox_f32": 3}
 REWARD = {"none": 0, "sp": 1, "batch": 2, "ocp": 3}
+OCP_MOMENTS = 4                     # pcg_desc.ocp_mode bit (PCG_OCP_MOMENTS)
 
 F_NORMALISE_A, F_NORMALISE_O, F_A_DELTA, F_R_PENALTY, F_DONE_ON_VIOLATION, F_ADAPTIVE, F_SP_HIDDEN = (1 << i for i in range(7))
 ST_NONFINITE, ST_STEPCAP = 1, 2

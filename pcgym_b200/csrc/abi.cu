@@ -167,7 +167,7 @@ int validate(const pcg_desc* d, const pcg_io* io, int64_t n_env, int64_t t0, int
   if (d->n_tail > 0 && !io->tail) return PCG_E_NULL;
   if ((d->flags & PCG_F_A_DELTA) && (d->flags & PCG_F_NORMALISE_A) && !io->a_save) return PCG_E_NULL;
   if (d->reward < 0 || d->reward > PCG_REWARD_OCP) return PCG_E_RANGE;
-  if (d->reward == PCG_REWARD_OCP && d->ocp_mode != 0 && !io->u_prev) return PCG_E_NULL;
+  if (d->reward == PCG_REWARD_OCP && (d->ocp_mode & 3) != 0 && !io->u_prev) return PCG_E_NULL;
   const void* ptrs[] = {io->x, io->a, io->a_save, io->z, io->tail, io->x_traj, io->obs, io->reward, io->g, io->g0,
                         io->h_carry, io->u_prev, io->theta};
   for (const void* p : ptrs)

@@ -56,8 +56,8 @@ inline int ept_override() {
 // the straight-line, software-pipelined kernel covers: fixed step with n_sub == 1, lean observation vector,
 // SP reward with <= 2 setpoints, <= 2 constraints, no a_delta, Philox / no noise, all trajectory outputs wanted
 template <class M>
-inline bool fast_ok(const pcg_desc& d, const pcg_io& io) {
-  if ((d.flags & PCG_F_ADAPTIVE) || d.n_sub != 1 || needs_general<M>(d)) return false;
+inline bool fast_ok(const pcg_desc& d, const pcg_io& io, bool adaptive = false) {
+  if (adaptive != ((d.flags & PCG_F_ADAPTIVE) != 0) || (!adaptive && d.n_sub != 1) || needs_general<M>(d)) return false;
   if ((d.flags & PCG_F_A_DELTA) && (d.flags & PCG_F_NORMALISE_A)) return false;
   if (d.reward != PCG_REWARD_SP || d.nsp < 1 || d.nsp > kFastNsp || d.n_con > kFastNcon) return false;
   if (d.noise == PCG_NOISE_EXTERNAL) return false;
@@ -183,7 +183,7 @@ inline bool wsm_ok(const pcg_desc& d, const pcg_io& io, int64_t n_env, int64_t k
   return tiles >= 2 && tiles <= kWsmMaxTiles;
 }
 
-template <class M, class TB, int NOISE, int NSP, bool CONU, bool SPS>
+template <class M, class TB, int NOISE, int NSP, bool CONU, bool SPS, bool ADAPT>
 cudaError_t launch_wsm_n(const pcg_desc& d, const pcg_io& io, const Derived<M, TB>& dv, int64_t n_env, int t0,
                          int k_steps, cudaStream_t s, int64_t epc, int n_tiles) {
   using Shared = WsmShared<M, NOISE, NSP, SPS>;
@@ -194,41 +194,42 @@ cudaError_t launch_wsm_n(const pcg_desc& d, const pcg_io& io, const Derived<M, T
   if (cudaGetDevice(&dev) != cudaSuccess) dev = 0;
   const uint64_t bit = uint64_t{1} << (dev & 63);
   if (!(opted.load(std::memory_order_acquire) & bit)) {
-    const cudaError_t attr = cudaFuncSetAttribute(wsm_rollout_kernel<M, TB, NOISE, NSP, CONU, SPS>,
+    const cudaError_t attr = cudaFuncSetAttribute(wsm_rollout_kernel<M, TB, NOISE, NSP, CONU, SPS, ADAPT>,
                                                   cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                   static_cast<int>(sizeof(Shared)));
     if (attr != cudaSuccess) return attr;
     opted.fetch_or(bit, std::memory_order_release);
   }
   const unsigned grid = static_cast<unsigned>((n_env + epc - 1) / epc);
-  wsm_rollout_kernel<M, TB, NOISE, NSP, CONU, SPS><<<grid, 32 * kWsmWarps, sizeof(Shared), s>>>(d, io, dv, n_env, t0,
-                                                                                            k_steps, epc, n_tiles);
+  wsm_rollout_kernel<M, TB, NOISE, NSP, CONU, SPS, ADAPT>
+      <<<grid, 32 * WsmLayout<ADAPT>::warps, sizeof(Shared), s>>>(d, io, dv, n_env, t0, k_steps, epc, n_tiles);
   return cudaGetLastError();
 }
 
-template <class M, class TB, int NSP, bool CONU, bool SPS>
+template <class M, class TB, int NSP, bool CONU, bool SPS, bool ADAPT>
 cudaError_t launch_wsm_s(const pcg_desc& d, const pcg_io& io, const Derived<M, TB>& dv, int64_t n_env, int t0,
                          int k_steps, cudaStream_t s, int64_t epc, int n_tiles) {
   switch (d.noise) {
     case PCG_NOISE_OFF:
-      return launch_wsm_n<M, TB, PCG_NOISE_OFF, NSP, CONU, SPS>(d, io, dv, n_env, t0, k_steps, s, epc, n_tiles);
+      return launch_wsm_n<M, TB, PCG_NOISE_OFF, NSP, CONU, SPS, ADAPT>(d, io, dv, n_env, t0, k_steps, s, epc, n_tiles);
     case PCG_NOISE_PHILOX:
-      return launch_wsm_n<M, TB, PCG_NOISE_PHILOX, NSP, CONU, SPS>(d, io, dv, n_env, t0, k_steps, s, epc, n_tiles);
+      return launch_wsm_n<M, TB, PCG_NOISE_PHILOX, NSP, CONU, SPS, ADAPT>(d, io, dv, n_env, t0, k_steps, s, epc, n_tiles);
     default:
-      return launch_wsm_n<M, TB, PCG_NOISE_PHILOX_F32, NSP, CONU, SPS>(d, io, dv, n_env, t0, k_steps, s, epc, n_tiles);
+      if constexpr (ADAPT) return cudaErrorNotSupported;       // launch_e keeps fp32-evaluated noise on the generic kernel
+      else return launch_wsm_n<M, TB, PCG_NOISE_PHILOX_F32, NSP, CONU, SPS, ADAPT>(d, io, dv, n_env, t0, k_steps, s, epc, n_tiles);
   }
 }
 
-template <class M, class TB, int NSP, bool CONU>
+template <class M, class TB, int NSP, bool CONU, bool ADAPT>
 cudaError_t launch_wsm_c(const pcg_desc& d, const pcg_io& io, const Derived<M, TB>& dv, int64_t n_env, int t0,
                          int k_steps, cudaStream_t s, int64_t epc, int n_tiles) {
   // the reference's setpoints are ONE schedule for every env (SP[k][t], pcgym.py:432-438): staged in shared memory
   const bool sps = io.sp_se == 0 && k_steps + 1 <= kWsmSpMax;
-  return sps ? launch_wsm_s<M, TB, NSP, CONU, true>(d, io, dv, n_env, t0, k_steps, s, epc, n_tiles)
-             : launch_wsm_s<M, TB, NSP, CONU, false>(d, io, dv, n_env, t0, k_steps, s, epc, n_tiles);
+  return sps ? launch_wsm_s<M, TB, NSP, CONU, true, ADAPT>(d, io, dv, n_env, t0, k_steps, s, epc, n_tiles)
+             : launch_wsm_s<M, TB, NSP, CONU, false, ADAPT>(d, io, dv, n_env, t0, k_steps, s, epc, n_tiles);
 }
 
-template <class M, class TB>
+template <class M, class TB, bool ADAPT = false>
 cudaError_t launch_wsm(const pcg_desc& d0, const pcg_io& io, int64_t n_env, int t0, int k_steps, cudaStream_t s,
                        int64_t epc, int n_tiles) {
   const pcg_desc d = fold_desc<M>(d0);
@@ -237,12 +238,13 @@ cudaError_t launch_wsm(const pcg_desc& d0, const pcg_io& io, int64_t n_env, int 
   for (int c = 0; c < d.n_con; ++c) con_u = con_u || d.con_mask_u[c] != 0;
   cudaError_t e;
   if (d.nsp == 1)
-    e = con_u ? launch_wsm_c<M, TB, 1, true>(d, io, dv, n_env, t0, k_steps, s, epc, n_tiles)
-              : launch_wsm_c<M, TB, 1, false>(d, io, dv, n_env, t0, k_steps, s, epc, n_tiles);
+    e = con_u ? launch_wsm_c<M, TB, 1, true, ADAPT>(d, io, dv, n_env, t0, k_steps, s, epc, n_tiles)
+              : launch_wsm_c<M, TB, 1, false, ADAPT>(d, io, dv, n_env, t0, k_steps, s, epc, n_tiles);
   else
-    e = con_u ? launch_wsm_c<M, TB, 2, true>(d, io, dv, n_env, t0, k_steps, s, epc, n_tiles)
-              : launch_wsm_c<M, TB, 2, false>(d, io, dv, n_env, t0, k_steps, s, epc, n_tiles);
-  t_last_kernel = "wsm_rollout_kernel (persistent CTA per SM: integrator warps + finisher pool)";
+    e = con_u ? launch_wsm_c<M, TB, 2, true, ADAPT>(d, io, dv, n_env, t0, k_steps, s, epc, n_tiles)
+              : launch_wsm_c<M, TB, 2, false, ADAPT>(d, io, dv, n_env, t0, k_steps, s, epc, n_tiles);
+  t_last_kernel = ADAPT ? "wsm_rollout_kernel (persistent CTA per SM, adaptive integrator warps + finisher pool)"
+                        : "wsm_rollout_kernel (persistent CTA per SM: integrator warps + finisher pool)";
   return e;
 }
 
@@ -289,6 +291,16 @@ cudaError_t launch_e(const pcg_desc& d, const pcg_io& io, int64_t n_env, int t0,
         if (two) return launch_fast<M, TB, 2>(d, io, n_env, t0, k_steps, s);
       }
       return launch_fast<M, TB, 1>(d, io, n_env, t0, k_steps, s);
+    }
+  }
+  if constexpr (ADAPTIVE && !GENERAL && M::FAST && M::EPT == 2 && TB::EMBEDDED) {
+    // the default scheme of make_env (adaptive embedded pair) in the integrator warps of the per-SM kernel
+    if constexpr (M::WS > 0) {
+      int64_t epc = 0;
+      int tiles = 0;
+      if (!generic && two && d.noise != PCG_NOISE_PHILOX_F32 && fast_ok<M>(d, io, true) &&
+          wsm_ok(d, io, n_env, k_steps, &epc, &tiles) && (req == PCG_KERNEL_WSM || req == PCG_KERNEL_AUTO))
+        return launch_wsm<typename M::WsModel, TB, true>(d, io, n_env, t0, k_steps, s, epc, tiles);
     }
   }
   if constexpr (!ADAPTIVE && M::EPT == 2) {

@@ -29,6 +29,18 @@ struct StepOut {               // what interval k leaves for its deferred epilog
   int t_new;
 };
 
+constexpr int kFastPf = 8;          // action-row prefetch distance in control intervals (ring slots per thread)
+
+template <int EPT>
+PCG_DEV void cp_async_row(double* smem, const double* gmem) {      // EPT doubles of this thread, global -> shared
+  const uint32_t sa = static_cast<uint32_t>(__cvta_generic_to_shared(smem));
+  if constexpr (EPT == 2) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem) : "memory");
+  else asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(gmem) : "memory");
+}
+PCG_DEV void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+PCG_DEV void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 template <class M, class TB, int NOISE, int EPT>
 __global__ void __launch_bounds__(kBlock, EPT == 1 ? M::MIN_BLOCKS_EPT1 : M::MIN_BLOCKS)
 fast_rollout_kernel(const __grid_constant__ pcg_desc d, const __grid_constant__ pcg_io io,
@@ -39,6 +51,12 @@ fast_rollout_kernel(const __grid_constant__ pcg_desc d, const __grid_constant__ 
     fill_icdf_tab(icdf_s);
     __syncthreads();
   }
+  // Action rows are staged through shared memory kFastPf intervals ahead with cp.async (global -> shared without a
+  // register in between; every thread reads back only the bytes it requested, so no barrier is involved): at
+  // 65 536 envs an SM holds ~7 warps of this kernel and a prefetch distance of ONE interval left every interval
+  // waiting for most of a DRAM round trip (ncu r2_fast_first_order_65k: long-scoreboard 2.9 of 4.0 stall cycles per
+  // issue, 34 % of the HBM roofline for the trivial first-order RHS).
+  __shared__ __align__(16) double a_ring[kFastPf][NU][kBlock * EPT];
   const int64_t env0 = (static_cast<int64_t>(blockIdx.x) * kBlock + threadIdx.x) * EPT;
   if (env0 >= n) return;
 
@@ -115,9 +133,22 @@ fast_rollout_kernel(const __grid_constant__ pcg_desc d, const __grid_constant__ 
     }
   };
 
-  double a_nxt[NU][EPT];
+  auto stage = [&](int k) {                        // action rows of interval k -> ring slot k % kFastPf (one group)
+    if (k < k_steps) {
 #pragma unroll
-  for (int j = 0; j < NU; ++j) ld_row<EPT>(pa + j * n, a_nxt[j]);
+      for (int j = 0; j < NU; ++j)
+        cp_async_row<EPT>(&a_ring[k % kFastPf][j][threadIdx.x * EPT], pa + (static_cast<int64_t>(k) * NU + j) * n);
+    }
+    cp_async_commit();                             // committed even when empty: interval k is always group k
+  };
+#pragma unroll
+  for (int k = 0; k < kFastPf; ++k) stage(k);
+  double a_nxt[NU][EPT];                           // interval 0 (also feeds the t == 0 pre-check)
+  cp_async_wait<kFastPf - 1>();
+#pragma unroll
+  for (int j = 0; j < NU; ++j)
+#pragma unroll
+    for (int e = 0; e < EPT; ++e) a_nxt[j][e] = a_ring[0][j][threadIdx.x * EPT + e];
 
   // ---- t == 0 pre-check (pcgym.py:416-420) with the first interval's input, outside the pipelined loop
   if (t0 == 0 && n_con > 0) {
@@ -186,14 +217,20 @@ fast_rollout_kernel(const __grid_constant__ pcg_desc d, const __grid_constant__ 
     StepOut<M, EPT> cur;
     cur.t_new = t + 1;                                                         // pcgym.py:441
     double a_raw[NU][EPT];
+    cp_async_wait<kFastPf - 1>();                                              // group k (this interval's rows) has landed
 #pragma unroll
-    for (int j = 0; j < NU; ++j)
-#pragma unroll
-      for (int e = 0; e < EPT; ++e) a_raw[j][e] = a_nxt[j][e];
-    // prefetch the next interval's actions / setpoints (clamped instead of branching at the end)
-    pa += (k + 1 < k_steps) ? static_cast<int64_t>(NU) * n : 0;
-#pragma unroll
-    for (int j = 0; j < NU; ++j) ld_row<EPT>(pa + j * n, a_nxt[j]);
+    for (int j = 0; j < NU; ++j) {
+      if constexpr (EPT == 2) {
+        const double2 v = *reinterpret_cast<const double2*>(&a_ring[k % kFastPf][j][threadIdx.x * 2]);
+        a_raw[j][0] = v.x;
+        a_raw[j][1] = v.y;
+      } else {
+        a_raw[j][0] = a_ring[k % kFastPf][j][threadIdx.x];
+      }
+    }
+    to_uk(a_raw, cur.uk);
+    stage(k + kFastPf);                                                        // refill the slot just read (same thread)
+    // next interval's setpoints (clamped instead of branching at the end)
 #pragma unroll
     for (int j = 0; j < kFastNsp; ++j) {
       psp[j] += (t + 2 < d.N) ? io.sp_st : 0;                                  // -> SP[min(t + 2, N - 1)]
@@ -205,7 +242,6 @@ fast_rollout_kernel(const __grid_constant__ pcg_desc d, const __grid_constant__ 
         sp_nxt[j][e] = psp[j][e * io.sp_se];
       }
     }
-    to_uk(a_raw, cur.uk);
 
     // Gaussian draws of this interval: a pure function of (seed, env, t)
 #pragma unroll

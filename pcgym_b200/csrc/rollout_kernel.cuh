@@ -159,15 +159,31 @@ PCG_DEV void rk_step_fixed(const Derived<M, TB>& dv, const typename M::Aux (&aux
 // different step counts; `max_steps` bounds the loop and a non-finite error estimate is treated as a
 // rejection so one bad lane cannot stall its warp.
 template <class M, class TB>
+PCG_DEV void advance_adaptive_aux(const Derived<M, TB>& dv, const typename M::P& mp, const typename M::Aux& aux,
+                                  double (&x)[M::NX], const double (&u)[M::NU + M::ND], double dt,
+                                  double rtol, double atol, int max_steps, double& h_carry, int& n_rhs,
+                                  unsigned& status);
+
+template <class M, class TB>
 PCG_DEV void advance_adaptive(const Derived<M, TB>& dv, const typename M::P& mp, double (&x)[M::NX],
                               const double (&u)[M::NU + M::ND], double dt,
                               double rtol, double atol, int max_steps, double& h_carry, int& n_rhs,
                               unsigned& status) {
+  typename M::Aux aux;
+  M::prep(mp, u, aux);
+  advance_adaptive_aux<M, TB>(dv, mp, aux, x, u, dt, rtol, atol, max_steps, h_carry, n_rhs, status);
+}
+
+// the same with the per-interval constants already prepared (the warp-specialised kernels bind their shared-memory
+// tables into `aux` first)
+template <class M, class TB>
+PCG_DEV void advance_adaptive_aux(const Derived<M, TB>& dv, const typename M::P& mp, const typename M::Aux& aux,
+                                  double (&x)[M::NX], const double (&u)[M::NU + M::ND], double dt,
+                                  double rtol, double atol, int max_steps, double& h_carry, int& n_rhs,
+                                  unsigned& status) {
   constexpr int NX = M::NX, S = TB::S;
   double t = 0.0;
   double h = (h_carry > 0.0 && h_carry < dt) ? h_carry : dt;
-  typename M::Aux aux;
-  M::prep(mp, u, aux);
   double k0[NX];
   M::rhs(mp, aux, x, u, k0);
   ++n_rhs;
@@ -344,7 +360,7 @@ rollout_kernel(const __grid_constant__ pcg_desc d, const __grid_constant__ pcg_i
 #pragma unroll
     for (int e = 0; e < EPT; ++e) u_prev[e][j] = v[e];
   }
-  bool u_prev_valid = d.ocp_mode != 2;
+  bool u_prev_valid = (d.ocp_mode & 3) != 2;
 
   // ---- per-thread stream pointers, advanced by a uniform stride every interval
   const double* pa = io.a + env0;
@@ -602,10 +618,19 @@ rollout_kernel(const __grid_constant__ pcg_desc d, const __grid_constant__ pcg_i
           if (j < nsp) {
             const int si = d.sp_state[j];
             double xo = 0.0;
+            if (NX >= 3 && (d.ocp_mode & PCG_OCP_MOMENTS)) {
+              // crystallization script (cryst_train.py:17-48): the tracked CV and Ln are DERIVED from the noisy
+              // moments, CV = sqrt(mu2 mu0 / mu1^2 - 1) against the first setpoint, Ln = mu1 / mu0 against the second
+              double o[3];
 #pragma unroll
-            for (int i = 0; i < NX; ++i) {
-              const double ox = fma(z[e][i] * x[e][i], d.noise_pct[i], x[e][i]);
-              xo = (si == i) ? ox : xo;
+              for (int i = 0; i < 3; ++i) o[i] = fma(z[e][i % NX] * x[e][i % NX], d.noise_pct[i % NX], x[e][i % NX]);
+              xo = (j == 0) ? sqrt(o[2] * o[0] / (o[1] * o[1]) - 1.0) : o[1] / o[0];
+            } else {
+#pragma unroll
+              for (int i = 0; i < NX; ++i) {
+                const double ox = fma(z[e][i] * x[e][i], d.noise_pct[i], x[e][i]);
+                xo = (si == i) ? ox : xo;
+              }
             }
             const double en = (xo - sp_nxt[j][e]) * d.ocp_inv_span[j];
             cost = fma(en * en, d.r_scale[j], cost);
@@ -615,7 +640,7 @@ rollout_kernel(const __grid_constant__ pcg_desc d, const __grid_constant__ pcg_i
           const double inv = 0.5 / d.a_scale[j];                               // 1 / (a_hi - a_lo)
           const double un = (uk[e][j] - (d.a_off[j] - d.a_scale[j])) * inv;
           const double up = ((u_prev_valid ? u_prev[e][j] : uk[e][j]) - (d.a_off[j] - d.a_scale[j])) * inv;
-          const double du = d.ocp_mode == 0 ? un : un - up;
+          const double du = (d.ocp_mode & 3) == 0 ? un : un - up;
           cost = fma(d.ocp_R * du, du, cost);
           u_prev[e][j] = uk[e][j];
         }

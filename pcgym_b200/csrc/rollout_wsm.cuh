@@ -65,6 +65,20 @@ constexpr int kWsmRing = 16;
 constexpr int kWsmMaxFin = 16;
 static_assert(kWsmRing >= kWsmMaxFin && (kWsmRing & (kWsmRing - 1)) == 0, "ring depth vs finisher count");
 
+// ADAPT = the integrator warps run the embedded pair with per-lane step-size control (advance_adaptive_aux: make_env's
+// default scheme).  The controller keeps six stage derivatives and two candidate states live and an interval costs
+// ~2.5 fixed steps, so the finishers have 2.5x less to do per unit time: 20 warps x 96 registers, 16 integrator-class
+// warps + 4 finishers, no register hand-over (setmaxnreg moves registers only inside the CTA's own allocation).
+template <bool ADAPT>
+struct WsmLayout {
+  static constexpr int warps = ADAPT ? 20 : kWsmWarps;
+  static constexpr int launch_regs = (65536 / (32 * warps)) / 8 * 8;
+  static constexpr int int_regs = ADAPT ? launch_regs : (PCG_WSM_INT_REGS ? PCG_WSM_INT_REGS : launch_regs);
+  static constexpr int fin_regs = ADAPT ? launch_regs : (PCG_WSM_INT_REGS ? PCG_WSM_FIN_REGS : launch_regs);
+  static_assert(16 * (launch_regs - int_regs) >= (warps - 16) * (fin_regs - launch_regs),
+                "setmaxnreg budgets do not fit the CTA's register allocation");
+};
+
 template <int N> PCG_DEV void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
 template <int N> PCG_DEV void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 
@@ -93,8 +107,8 @@ struct WsmShared {
 // NSP = number of setpoints (1 or 2), CONU = some constraint reads an input, SPS = the setpoint schedule is shared by
 // all envs and short enough to be staged in shared memory: compile-time, so the finisher carries no dead reward /
 // setpoint / input-column work and no branch for it
-template <class M, class TB, int NOISE, int NSP, bool CONU, bool SPS>
-__global__ void __launch_bounds__(32 * kWsmWarps, 1)
+template <class M, class TB, int NOISE, int NSP, bool CONU, bool SPS, bool ADAPT = false>
+__global__ void __launch_bounds__(32 * WsmLayout<ADAPT>::warps, 1)
 wsm_rollout_kernel(const __grid_constant__ pcg_desc d, const __grid_constant__ pcg_io io,
                    const __grid_constant__ Derived<M, TB> dv, const int64_t n, const int t0, const int k_steps,
                    const int64_t envs_per_cta, const int n_tiles) {
@@ -147,9 +161,11 @@ wsm_rollout_kernel(const __grid_constant__ pcg_desc d, const __grid_constant__ p
 
   // first finisher warp / number of finishers (warps between the two roles, and past the last finisher, retire)
   const int fin0 = kWsmIntClass ? kWsmIntClass : n_int;
-  const int n_fin = (kWsmWarps - fin0) < kWsmMaxFin ? (kWsmWarps - fin0) : kWsmMaxFin;
+  using L = WsmLayout<ADAPT>;
+  static_assert(!ADAPT || (EPI == 1 && TB::EMBEDDED), "adaptive integrator warps carry one env per lane");
+  const int n_fin = (L::warps - fin0) < kWsmMaxFin ? (L::warps - fin0) : kWsmMaxFin;
   if (warp < fin0) {
-    if constexpr (kWsmIntClass != 0) setmaxnreg_dec<PCG_WSM_INT_REGS>();                     // whole warpgroups: warps 0..15
+    if constexpr (kWsmIntClass != 0 && L::int_regs < L::launch_regs) setmaxnreg_dec<L::int_regs>();   // whole warpgroups: warps 0..15
     if (warp >= n_int) return;
     // ================================================================ integrator warp: tile p, env 2 lane + h (+ e)
     const int p = warp / IPT, h = (warp % IPT) * EPI;
@@ -164,6 +180,10 @@ wsm_rollout_kernel(const __grid_constant__ pcg_desc d, const __grid_constant__ p
 #pragma unroll
       for (int e = 0; e < EPI; ++e) x[e][i] = v[e];
     }
+    // adaptive mode: the step size carried from interval to interval, RHS evaluations and status bits of this lane's env
+    double h_carry = (ADAPT && io.h_carry) ? io.h_carry[env0] : 0.0;
+    int n_rhs = 0;
+    unsigned st_adapt = 0;
     // the finishers read the initial state for the t == 0 pre-check before they release interval 0, so io.x may be
     // overwritten at the end without a race
 #pragma unroll 1
@@ -185,7 +205,11 @@ wsm_rollout_kernel(const __grid_constant__ pcg_desc d, const __grid_constant__ p
         M::prep(dv.p, uk[e], aux[e]);
         bind_exp_tab<M>(aux[e], sh.exp_tab);
       }
-      rk_step_fixed<M, TB, EPI>(dv, aux, x, uk);                               // integrator.py:90-107
+      if constexpr (ADAPT) {                                                   // integrator.py:65-88 (Tsit5 + PID 1e-8)
+        advance_adaptive_aux<M, TB>(dv, dv.p, aux[0], x[0], uk[0], d.dt, d.rtol, d.atol, d.max_steps, h_carry, n_rhs, st_adapt);
+      } else {
+        rk_step_fixed<M, TB, EPI>(dv, aux, x, uk);                             // integrator.py:90-107
+      }
 #pragma unroll
       for (int i = 0; i < NX; ++i)
 #pragma unroll
@@ -194,20 +218,21 @@ wsm_rollout_kernel(const __grid_constant__ pcg_desc d, const __grid_constant__ p
     }
 #pragma unroll
     for (int e = 0; e < EPI; ++e) {
-      unsigned status = 0;
+      unsigned status = st_adapt;
 #pragma unroll
       for (int i = 0; i < NX; ++i) {
         if (!isfinite(x[e][i])) status |= PCG_ST_NONFINITE;
         io.x[i * n + env0 + e] = x[e][i];
       }
       if (io.status && status) io.status[env0 + e] |= static_cast<uint8_t>(status);
-      if (io.n_rhs) io.n_rhs[env0 + e] += k_steps * TB::S;
+      if (io.n_rhs) io.n_rhs[env0 + e] += ADAPT ? n_rhs : k_steps * TB::S;
     }
+    if (ADAPT && io.h_carry) io.h_carry[env0] = h_carry;
     return;
   }
 
   // ================================================================== finisher pool
-  if constexpr (kWsmIntClass != 0) setmaxnreg_inc<PCG_WSM_FIN_REGS>();                       // whole warpgroups: warps 16 and up
+  if constexpr (kWsmIntClass != 0 && L::fin_regs > L::launch_regs) setmaxnreg_inc<L::fin_regs>();                       // whole warpgroups: warps 16 and up
   const int fin = warp - fin0;
   if (fin >= n_fin) return;
   const int flags = d.flags;

@@ -83,10 +83,18 @@ class make_env:
             self.reward = None
             if isinstance(self.custom_reward_f, dict):
                 # declarative form of the paper scripts' reward: fused into the kernel (PCG_REWARD_OCP)
+                # kind "ocp_tracking": custom_reward.py:3-39 / 4tank_train.py:16-52; kind "cryst_tracking": the
+                # crystallization script's variant (cryst_train.py:17-48), which tracks CV and Ln DERIVED from the
+                # noisy moments against the first and second setpoint (R defaults to that script's 0.01)
                 spec = dict(self.custom_reward_f)
-                if spec.pop("kind", "ocp_tracking") != "ocp_tracking":
-                    raise ValueError("custom_reward dict: only kind='ocp_tracking' is known")
-                self._ocp = {"R": float(spec.pop("R", 0.1)), "delta_u": bool(spec.pop("delta_u", True))}
+                kind = spec.pop("kind", "ocp_tracking")
+                if kind not in ("ocp_tracking", "cryst_tracking"):
+                    raise ValueError("custom_reward dict: kind must be 'ocp_tracking' or 'cryst_tracking'")
+                self._ocp = {"R": float(spec.pop("R", 0.1 if kind == "ocp_tracking" else 0.01)),
+                             "delta_u": bool(spec.pop("delta_u", True)), "moments": kind == "cryst_tracking"}
+                if self._ocp["moments"] and (P.get("model") != "crystallization" or len(self.SP or {}) != 2):
+                    raise ValueError("custom_reward kind='cryst_tracking' is the crystallization model's reward "
+                                     "(two setpoints: CV, Ln)")
                 if spec:
                     raise ValueError(f"custom_reward dict: unknown keys {sorted(spec)}")
                 if self.SP is None:
@@ -456,7 +464,7 @@ class make_env:
         if self._ocp is not None:
             d.reward = nat.REWARD["ocp"]
             d.ocp_R = self._ocp["R"]
-            d.ocp_mode = 2 if self._ocp["delta_u"] else 0
+            d.ocp_mode = (2 if self._ocp["delta_u"] else 0) | (nat.OCP_MOMENTS if self._ocp["moments"] else 0)
             for j, k in enumerate(self._sp_keys):
                 i = names.index(k)
                 d.ocp_inv_span[j] = 1.0 / (hi[i] - lo[i])
@@ -601,6 +609,7 @@ class make_env:
             for idx, unc in enumerate(self.uncertainty_percentages["x0"]):         # iterates keys, as :286-288
                 x0[idx] = self._perturb(x0[idx], float(unc), gen)
         self._x.copy_(x0[:nx])
+        self._x_reset = x0[:nx]                                                    # rewind(to_x0=True) restores it
         parts = [x0]                                                               # [x | SP slots of x0]
         if self.disturbance_active and self._d_keys:
             d0 = self._d_dev[0] if self._d_per_env else self._d_dev[:, 0:1].expand(-1, n)
@@ -621,7 +630,8 @@ class make_env:
                     self._theta[self._theta_names.index(name)] = self._tail[j]
         if self.a_delta:
             self.a_save_init = _np(self.a_0).reshape(-1)
-            self._a_save.copy_(torch.as_tensor(self.a_save_init, device=self.device)[:, None].expand(-1, n))
+            self._a_save0 = torch.as_tensor(self.a_save_init, device=self.device)[:, None].expand(-1, n).contiguous()
+            self._a_save.copy_(self._a_save0)
         self._state0 = torch.cat(parts, dim=0)                                     # [n_obs, n]
         self._done_state.zero_()
         self._status.zero_()
@@ -956,20 +966,27 @@ class make_env:
             nat.check(nat.lib().pcg_rollout(ctypes.byref(d), ctypes.byref(io), self.n_envs, self.t, K,
                                             ctypes.c_void_p(stream)))
         self.t += K
-        if d.ocp_mode == 2:                  # io.u_prev is valid from now on (it survives reset(), as `self.u_prev` does)
-            self._desc.ocp_mode = self._desc_step.ocp_mode = 1
+        if d.ocp_mode & 3 == 2:              # io.u_prev is valid from now on (it survives reset(), as `self.u_prev` does)
+            self._desc.ocp_mode = self._desc_step.ocp_mode = (d.ocp_mode & ~3) | 1
         return bufs
 
-    def rewind(self, t: int = 0, episode=None):
+    def rewind(self, t: int = 0, episode=None, to_x0: bool = False):
         """Begin a new episode from the CURRENT device state: only the time index and the sticky done flag
         are cleared (no x0 copy, no allocation) and the noise key moves on to the next episode (or to `episode`).
-        Continuing-task rollouts and the benchmark use this."""
+        Continuing-task rollouts and the headline benchmark use this.  `to_x0=True` also puts back the model state
+        (and the a_delta accumulator) the last reset() produced -- one device-to-device copy, no host work and no new
+        random draws: what a benchmark pass over a model that does not survive arbitrary action sequences for long
+        (crystallization) starts from.  `status` is NOT cleared (only reset() does), so trouble in any pass stays visible."""
         if not self._dev_ready:
             raise RuntimeError("call reset() before rewind()")
         self._begin_episode(episode)
         self.t = int(t)
         self._done_state.zero_()
         self.done = False
+        if to_x0:
+            self._x.copy_(self._x_reset)
+            if self.a_delta:
+                self._a_save.copy_(self._a_save0)
 
     # ------------------------------------------------------------------ reference attributes
     @property
