@@ -69,7 +69,10 @@ enum pcg_model {
    * probed on the host and run by these; id = BASE + (nx - 1) * PCG_AFFINE_MAX_NU + (nu - 1);
    * theta = A row-major (nx*nx), B row-major (nx*nu), c (nx); Tsit5 only. */
   PCG_MODEL_AFFINE_BASE = 19,
-  PCG_MODEL_COUNT = 27
+  /* EXTENSION, not a reference model: ten stages of multistage_extraction's stage balances (20 states), for
+   * BASELINE.json config 4's wording "10-stage, ~20-state"; the reference column has five (model_classes.py:381,424) */
+  PCG_MODEL_EXTRACTION_10 = 27,   /* "multistage_extraction_10stage" */
+  PCG_MODEL_COUNT = 28
 };
 
 /* integrator: replaces integrator.py:90-107 (CVODES) / :65-88 (diffrax Tsit5 + PID 1e-8) */
@@ -77,7 +80,10 @@ enum pcg_scheme {
   PCG_SCHEME_RK4 = 0,     /* classical RK4, fixed step only                         */
   PCG_SCHEME_DOPRI5 = 1,  /* Dormand-Prince 5(4) ("RK45")                           */
   PCG_SCHEME_TSIT5 = 2,   /* Tsitouras 5(4), the pair the reference's jax path uses */
-  PCG_SCHEME_COUNT = 3
+  PCG_SCHEME_RODAS4 = 3,  /* RODAS4 Rosenbrock 4(3), L-stable, analytic Jacobian: the stiff counterpart of the
+                             reference's CVODES BDF (integrator.py:163-182); adaptive only; models that provide
+                             the Jacobian (pcg_model_stiff_capable)                  */
+  PCG_SCHEME_COUNT = 4
 };
 
 enum pcg_noise {
@@ -249,6 +255,8 @@ int pcg_sizeof_io(void);
 /* Dimensions of a registry model: states, manipulated inputs, disturbance channels, parameters.
  * Replaces the reference's model.info() lookups (model_classes.py:11-20). */
 int pcg_model_dims(int model, int* nx, int* nu, int* nd, int* nparam);
+/* 1 if the model provides the analytic Jacobian PCG_SCHEME_RODAS4 needs (cstr, multistage_extraction), else 0 */
+int pcg_model_stiff_capable(int model);
 
 /* Name and default of parameter `i` of `model` (reference dataclass field order); NULL if out of range. */
 const char* pcg_model_param_name(int model, int i);

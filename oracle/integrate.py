@@ -20,6 +20,12 @@ parity target (CVODES at its default tolerances is itself only ~1e-5 accurate).
                   one Tsit5 step per control interval is compared with this at
                   ~1e-12 (same scheme, different arithmetic order) and with the
                   converged solution at the north-star rtol 1e-6.
+  advance_rodas4  the RODAS4 Rosenbrock 4(3) method with step-size control and a
+                  finite-difference Jacobian, one env at a time: the same-scheme
+                  check of the kernels' stiff integrator (scheme "rodas4"), which
+                  stands in for the reference's CVODES BDF (integrator.py:163-182)
+                  where the dynamics are stiff (an ignited cstr).  The converged
+                  reference for such cases is advance_truth(method="Radau").
 """
 from __future__ import annotations
 
@@ -118,3 +124,81 @@ def advance_fixed(model, x, u, dt, p=None, scheme="tsit5", n_sub=1):
             if b != 0.0:
                 x = x + (h * b) * kj
     return x
+
+
+# RODAS4 (Hairer & Wanner, Solving ODEs II, sec. IV.7; coefficients of rodas.f), transformed form:
+#   W = I / (gamma h) - J(y0);   W U_i = f(y0 + sum_j a_ij U_j) + sum_j (c_ij / h) U_j;   y1 = y0 + sum_j a_5j U_j + U_6
+RODAS4 = {
+    "gamma": 0.25,
+    "A": [[],
+          [0.1544e1],
+          [0.9466785280815826, 0.2557011698983284],
+          [0.3314825187068521e1, 0.2896124015972201e1, 0.9986419139977817],
+          [0.1221224509226641e1, 0.6019134481288629e1, 0.1253708332932087e2, -0.6878860361058950],
+          [0.1221224509226641e1, 0.6019134481288629e1, 0.1253708332932087e2, -0.6878860361058950, 1.0]],
+    "C": [[],
+          [-0.56688e1],
+          [-0.2430093356833875e1, -0.2063599157091915],
+          [-0.1073529058151375, -0.9594562251023355e1, -0.2047028614809616e2],
+          [0.7496443313967647e1, -0.1024680431464352e2, -0.3399990352819905e2, 0.1170890893206160e2],
+          [0.8083246795921522e1, -0.7981132988064893e1, -0.3152159432874371e2, 0.1631930543123136e2,
+           -0.6058818238834054e1]],
+}
+
+
+def _fd_jacobian(f, x, u):
+    """Central differences with a state-scaled increment (~1e-9 relative: the effect on a RODAS4 step is far below
+    the step-size controller's tolerance; the kernels use the analytic Jacobian)."""
+    n = x.shape[0]
+    J = np.empty((n, n))
+    for j in range(n):
+        d = 1e-6 * max(abs(x[j]), 1e-3)
+        e = np.zeros(n)
+        e[j] = d
+        J[:, j] = (f(x + e, u) - f(x - e, u)) / (2 * d)
+    return J
+
+
+def rodas4_step(f, J, x, u, h):
+    """One RODAS4 step of size h from x with Jacobian matrix J: returns (x_new, error estimate U_6)."""
+    n = x.shape[0]
+    W = np.eye(n) / (RODAS4["gamma"] * h) - J
+    U = []
+    xi = x
+    for a_row, c_row in zip(RODAS4["A"], RODAS4["C"]):
+        xi = x + sum((a * Uj for a, Uj in zip(a_row, U)), np.zeros(n))
+        rhs = f(xi, u) + sum(((c / h) * Uj for c, Uj in zip(c_row, U)), np.zeros(n))
+        U.append(np.linalg.solve(W, rhs))
+    return xi + U[-1], U[-1]
+
+
+def advance_rodas4(model, x, u, dt, p=None, rtol=1e-8, atol=1e-8, h0=None, jac=None, max_steps=100000):
+    """x(dt) for ONE env by step-size-controlled RODAS4 (controller of the kernels: err = RMS(U_6 / (atol + rtol max(|x|,
+    |x'|))), h *= clamp(0.9 err^-1/4, 0.2, 6), no growth right after a rejection).  Returns (x, h_carry, steps)."""
+    f = _as_fun(model, p)
+    x = np.asarray(x, dtype=np.float64).copy()
+    u = np.asarray(u, dtype=np.float64)
+    t, h = 0.0, (h0 if (h0 is not None and 0 < h0 < dt) else 0.25 * dt)
+    steps, rejected = 0, False
+    while t < dt:
+        steps += 1
+        if steps > max_steps:
+            raise RuntimeError("advance_rodas4: step cap")
+        left = dt - t
+        last = h >= left * (1 - 1e-12)
+        hh = left if last else h
+        J = jac(x, u) if jac is not None else _fd_jacobian(f, x, u)
+        xn, err = rodas4_step(f, J, x, u, hh)
+        sc = atol + rtol * np.maximum(np.abs(x), np.abs(xn))
+        msq = float(np.mean((err / sc) ** 2))
+        grow = 0.9 * max(msq, 1e-30) ** -0.125 if np.isfinite(msq) else 0.2
+        if np.isfinite(msq) and msq <= 1.0:
+            t = dt if last else t + hh
+            x = xn
+            hn = hh * min(1.0 if rejected else 6.0, grow)
+            h = max(h, hn) if last else hn
+            rejected = False
+        else:
+            h = hh * max(0.2, min(grow, 1.0))
+            rejected = True
+    return x, h, steps

@@ -35,6 +35,12 @@ MODELS = {
         inputs=["L", "G"], disturbances=["X0", "Y6"],
         params=dict(Vl=5.0, Vg=5.0, m=1.0, Kla=5.0, eq_exponent=2.0, X0=0.6, Y6=0.05),
     ),
+    # extension: ten stages of the same balances (see multistage_extraction_10stage)
+    "multistage_extraction_10stage": dict(
+        states=[f"{s}{k}" for k in range(1, 11) for s in ("X", "Y")],
+        inputs=["L", "G"], disturbances=["X0", "Y11"],
+        params=dict(Vl=5.0, Vg=5.0, m=1.0, Kla=5.0, eq_exponent=2.0, X0=0.6, Y11=0.05),
+    ),
     # model_classes.py:864-931
     "four_tank": dict(
         states=["h1", "h2", "h3", "h4"], inputs=["v1", "v2"], disturbances=["None"],
@@ -110,6 +116,16 @@ def multistage_extraction(x, u, p):
         out[2 * i] = (1.0 / p["Vl"]) * (L * (x_in - X[i]) - Q)
         out[2 * i + 1] = (1.0 / p["Vg"]) * (G * (y_in - Y[i]) + Q)
     return out
+
+
+def multistage_extraction_10stage(x, u, p):
+    """EXTENSION (BASELINE.json config 4 words the workload "10-stage, ~20-state"; the reference column has five
+    stages, model_classes.py:381,424): the SAME stage balances (:387-410) for ten stages, gas feed Y11.  There is no
+    reference implementation of this size; tests pin it through the five-stage code path it shares and the column's
+    overall mass balance."""
+    q = dict(p)
+    q["Y6"] = q.pop("Y11")
+    return multistage_extraction(x, u, q)
 
 
 def four_tank(x, u, p):
@@ -414,6 +430,7 @@ RHS = {
     "cstr": cstr,
     "first_order_system": first_order_system,
     "multistage_extraction": multistage_extraction,
+    "multistage_extraction_10stage": multistage_extraction_10stage,
     "four_tank": four_tank,
     "biofilm_reactor": biofilm_reactor,
     "crystallization": crystallization,

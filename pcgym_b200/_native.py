@@ -36,8 +36,9 @@ MODEL_IDS = {
     "coupled_oscillator": 16,
     "disease": 17,
     "hydraulic_tank": 18,
+    "multistage_extraction_10stage": 27,       # extension (ids 19..26 are the affine custom models)
 }
-SCHEMES = {"rk4": 0, "dopri5": 1, "rk45": 1, "tsit5": 2}
+SCHEMES = {"rk4": 0, "dopri5": 1, "rk45": 1, "tsit5": 2, "rodas4": 3}
 NOISE = {"off": 0, "philox": 1, "external": 2, "philox_f32": 3}
 REWARD = {"none": 0, "sp": 1, "batch": 2, "ocp": 3}
 OCP_MOMENTS = 4                     # pcg_desc.ocp_mode bit (PCG_OCP_MOMENTS)
@@ -98,6 +99,7 @@ SYMBOLS = {
     "pcg_sizeof_desc": (C.c_int, []),
     "pcg_sizeof_io": (C.c_int, []),
     "pcg_model_dims": (C.c_int, [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "pcg_model_stiff_capable": (C.c_int, [C.c_int]),
     "pcg_model_param_name": (C.c_char_p, [C.c_int, C.c_int]),
     "pcg_model_param_default": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_double)]),
     "pcg_step": (C.c_int, [C.POINTER(Desc), C.POINTER(IO), C.c_int64, C.c_int64, C.c_void_p]),

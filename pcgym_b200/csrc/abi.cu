@@ -13,6 +13,7 @@ struct ModelInfo {
   const char* const* names;
   const double* defaults;
   pcg::launch_fn launch;
+  bool stiff = false;        // provides the Rosenbrock interface (PCG_SCHEME_RODAS4)
 };
 
 // parameter names / defaults in reference dataclass field order (model_classes.py)
@@ -22,6 +23,7 @@ const char* const kFoN[] = {"K", "tau"};
 const double kFoD[] = {1, 0.5};
 const char* const kExN[] = {"Vl", "Vg", "m", "Kla", "eq_exponent", "X0", "Y6"};
 const double kExD[] = {5, 5, 1, 5, 2, 0.6, 0.05};
+const char* const kEx10N[] = {"Vl", "Vg", "m", "Kla", "eq_exponent", "X0", "Y11"};
 const char* const kFtN[] = {"g", "gamma_1", "gamma_2", "k1", "k2", "a1", "a2", "a3", "a4", "A1", "A2", "A3", "A4"};
 const double kFtD[] = {9.81, 0.2, 0.2, 0.00085, 0.00095, 0.0035, 0.0030, 0.0020, 0.0025, 1, 1, 1, 1};
 const char* const kCrN[] = {"ka", "kb", "kc", "kd", "kg", "k1", "k2", "a", "b", "alfa", "ro"};
@@ -86,7 +88,7 @@ ModelInfo affine_info() {
 
 template <class M>
 constexpr ModelInfo info(const char* const* n, const double* dflt, pcg::launch_fn f) {
-  return ModelInfo{M::NX, M::NU, M::ND, M::NP, n, dflt, f};
+  return ModelInfo{M::NX, M::NU, M::ND, M::NP, n, dflt, f, pcg::is_stiff_capable<M>::value};
 }
 
 const ModelInfo kModels[PCG_MODEL_COUNT] = {
@@ -111,6 +113,7 @@ const ModelInfo kModels[PCG_MODEL_COUNT] = {
     info<pcg::HydraulicTank>(kHtN, kHtD, pcg::launch_hydraulic_tank),
     PCG_AFFINE_ROW(1, 1), PCG_AFFINE_ROW(1, 2), PCG_AFFINE_ROW(2, 1), PCG_AFFINE_ROW(2, 2),
     PCG_AFFINE_ROW(3, 1), PCG_AFFINE_ROW(3, 2), PCG_AFFINE_ROW(4, 1), PCG_AFFINE_ROW(4, 2),
+    info<pcg::Extraction10>(kEx10N, kExD, pcg::launch_extraction10),       // extension, after the affine block (ids are ABI)
 };
 
 // the measurement-noise transform on caller-supplied Philox words (pcg_normal_pairs)
@@ -137,6 +140,7 @@ int validate(const pcg_desc* d, const pcg_io* io, int64_t n_env, int64_t t0, int
   if (d->scheme < 0 || d->scheme >= PCG_SCHEME_COUNT) return PCG_E_SCHEME;
   const bool adaptive = (d->flags & PCG_F_ADAPTIVE) != 0;
   if (adaptive && d->scheme == PCG_SCHEME_RK4) return PCG_E_SCHEME;
+  if (d->scheme == PCG_SCHEME_RODAS4 && (!adaptive || !kModels[d->model].stiff)) return PCG_E_SCHEME;   // adaptive, Jacobian needed
   if (d->model >= PCG_MODEL_AFFINE_BASE && d->scheme != PCG_SCHEME_TSIT5) return PCG_E_SCHEME;   // Tsit5 kernels only
   const ModelInfo& m = kModels[d->model];
   if (d->nu_a != m.nu) return PCG_E_DIMS;
@@ -191,6 +195,10 @@ int pcg_model_dims(int model, int* nx, int* nu, int* nd, int* nparam) {
   if (nd) *nd = m.nd;
   if (nparam) *nparam = m.np;
   return PCG_OK;
+}
+
+int pcg_model_stiff_capable(int model) {
+  return (model >= 0 && model < PCG_MODEL_COUNT && kModels[model].stiff) ? 1 : 0;
 }
 
 const char* pcg_model_param_name(int model, int i) {

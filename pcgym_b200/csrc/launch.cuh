@@ -293,7 +293,7 @@ cudaError_t launch_e(const pcg_desc& d, const pcg_io& io, int64_t n_env, int t0,
       return launch_fast<M, TB, 1>(d, io, n_env, t0, k_steps, s);
     }
   }
-  if constexpr (ADAPTIVE && !GENERAL && M::FAST && M::EPT == 2 && TB::EMBEDDED) {
+  if constexpr (ADAPTIVE && !GENERAL && M::FAST && M::EPT == 2 && TB::EMBEDDED && !is_rosenbrock<TB>::value) {
     // the default scheme of make_env (adaptive embedded pair) in the integrator warps of the per-SM kernel
     if constexpr (M::WS > 0) {
       int64_t epc = 0;
@@ -336,6 +336,9 @@ cudaError_t launch_model(const pcg_desc& d, const pcg_io& io, int64_t n_env, int
     case PCG_SCHEME_TSIT5:
       return adaptive ? launch_g<M, Tsit5, true>(d, io, n_env, t0, k_steps, s)
                       : launch_g<M, Tsit5, false>(d, io, n_env, t0, k_steps, s);
+    case PCG_SCHEME_RODAS4:                       // always adaptive; models with the Rosenbrock interface (abi.cu validates)
+      if constexpr (is_stiff_capable<M>::value) return launch_g<M, Rodas4, true>(d, io, n_env, t0, k_steps, s);
+      else return cudaErrorInvalidValue;
   }
   return cudaErrorInvalidValue;
 }
@@ -344,6 +347,7 @@ cudaError_t launch_model(const pcg_desc& d, const pcg_io& io, int64_t n_env, int
 cudaError_t launch_cstr(const pcg_desc&, const pcg_io&, int64_t, int, int, cudaStream_t);
 cudaError_t launch_first_order(const pcg_desc&, const pcg_io&, int64_t, int, int, cudaStream_t);
 cudaError_t launch_extraction(const pcg_desc&, const pcg_io&, int64_t, int, int, cudaStream_t);
+cudaError_t launch_extraction10(const pcg_desc&, const pcg_io&, int64_t, int, int, cudaStream_t);
 cudaError_t launch_four_tank(const pcg_desc&, const pcg_io&, int64_t, int, int, cudaStream_t);
 cudaError_t launch_crystallization(const pcg_desc&, const pcg_io&, int64_t, int, int, cudaStream_t);
 cudaError_t launch_biofilm(const pcg_desc&, const pcg_io&, int64_t, int, int, cudaStream_t);

@@ -60,6 +60,26 @@ struct Cstr {
     dx[0] = fma(-p.thru, ca, a.feed_c) - rate;                                   // :53
     dx[1] = fma(p.c_heat, rate, fma(p.c_T, T, a.heat0));                         // :54-58
   }
+  // Rosenbrock interface (scheme "rodas4"): W = s I - J(x) with the analytic Jacobian of the two lines above, kept as
+  // its 2 x 2 inverse.  dk/dT = k E/(R T^2).
+  static constexpr bool STIFF = true;
+  struct Lin { double i00, i01, i10, i11; };
+  PCG_DEV static void factor(const P& p, const Aux&, const double* x, const double*, double s, Lin& w) {
+    const double ca = x[0], T = x[1];
+    const double r = rcp_nr(T);
+    const double k = exp_sat(fma(p.neg_ear, r, p.ln_k0));
+    const double dr = -p.neg_ear * r * r * k * ca;               // d(k ca)/dT
+    const double w00 = s + p.thru + k, w01 = dr;                 // -J00, -J01
+    const double w10 = -p.c_heat * k, w11 = s - fma(p.c_heat, dr, p.c_T);
+    const double idet = rcp_nr(fma(w00, w11, -(w01 * w10)));
+    w.i00 = w11 * idet;  w.i01 = -w01 * idet;
+    w.i10 = -w10 * idet; w.i11 = w00 * idet;
+  }
+  PCG_DEV static void solve(const Lin& w, double* b) {
+    const double b0 = b[0], b1 = b[1];
+    b[0] = fma(w.i00, b0, w.i01 * b1);
+    b[1] = fma(w.i10, b0, w.i11 * b1);
+  }
 };
 
 // cstr with the Horner-form exponential (integrator warps of the warp-specialised kernel)
@@ -98,6 +118,12 @@ struct CstrT : Cstr {
 
 // ---------------------------------------------------------------------------------------
 // first_order_system -- model_classes.py:296-343      theta: K tau
+// models with the Rosenbrock interface (STIFF, Lin, factor, solve)
+template <class M, class = void>
+struct is_stiff_capable { static constexpr bool value = false; };
+template <class M>
+struct is_stiff_capable<M, decltype(void(M::STIFF))> { static constexpr bool value = true; };
+
 struct FirstOrder {
   static constexpr int NX = 1, NU = 1, ND = 0, NP = 2;
   struct P { double K, inv_tau; };
@@ -118,8 +144,11 @@ struct FirstOrder {
 // multistage_extraction -- model_classes.py:346-430
 // theta: Vl Vg m Kla eq_exponent X0 Y6                 disturbances: X0, Y6
 // states interleaved X1 Y1 ... X5 Y5
-struct Extraction {
-  static constexpr int NSTAGE = 5;
+// ExtractionT<5> is the reference model; ExtractionT<10> ("multistage_extraction_10stage") is an EXTENSION with the same
+// stage balances (BASELINE.json config 4 words the workload "10-stage, ~20-state"; the reference has no such model).
+template <int NS>
+struct ExtractionT {
+  static constexpr int NSTAGE = NS;
   static constexpr int NX = 2 * NSTAGE, NU = 2, ND = 2, NP = 7;
   struct P { double inv_vl, inv_vg, inv_m, kla_vl, expo; bool square; };
   PCG_HD static P make(const double* th) {
@@ -135,8 +164,8 @@ struct Extraction {
   struct Aux {};
   PCG_DEV static void prep(const P&, const double*, Aux&) {}
   PCG_HD static constexpr int dpar(int i) { constexpr int t[] = {5, 6}; return t[i]; }
-  static constexpr int EPT = 1, MIN_BLOCKS = 4, MIN_BLOCKS_EPT1 = 4, WS = 0;
-  static constexpr bool FAST = true;
+  static constexpr int EPT = 1, MIN_BLOCKS = NS <= 5 ? 4 : 2, MIN_BLOCKS_EPT1 = NS <= 5 ? 4 : 2, WS = 0;
+  static constexpr bool FAST = NS <= 5;           // the straight-line kernel keeps two intervals of state in registers
   PCG_DEV static void rhs(const P& p, const Aux&, const double* x, const double* u, double* dx) {
     const double L = u[0], G = u[1], X0 = u[2], Y6 = u[3];
 #pragma unroll
@@ -150,7 +179,64 @@ struct Extraction {
       dx[2 * i + 1] = p.inv_vg * fma(G, yin - Y, Q);
     }
   }
+  // Rosenbrock interface (scheme "rodas4"): with the states interleaved X1 Y1 X2 Y2 ... the Jacobian of the column is
+  // pentadiagonal (X_i sees X_{i-1} two columns to the left and Y_i one to the right; Y_i sees X_i one to the left and
+  // Y_{i+1} two to the right).  W = s I - J is a column-diagonally-dominant Z-matrix (the stage balances conserve mass),
+  // so the banded LU needs no pivoting; it is kept as unit-lower multipliers, the upper band and reciprocal pivots.
+  static constexpr bool STIFF = true;
+  struct Lin { double l1[NX], l2[NX], u1[NX], u2[NX], ip[NX]; };
+  PCG_DEV static void factor(const P& p, const Aux&, const double* x, const double* u, double s, Lin& w) {
+    const double L = u[0], G = u[1];
+    double d[NX], a1[NX], a2[NX], b1[NX], b2[NX];        // diagonal, sub-1, sub-2, super-1, super-2 of W
+#pragma unroll
+    for (int i = 0; i < NSTAGE; ++i) {
+      const double Y = x[2 * i + 1];
+      const double dye = (p.square ? 2.0 * Y : p.expo * pow(Y, p.expo - 1.0)) * p.inv_m;     // d(Y^e / m)/dY
+      const double q = p.kla_vl * dye;
+      d[2 * i] = s + p.inv_vl * (L + p.kla_vl);
+      a1[2 * i] = 0.0;  a2[2 * i] = -(p.inv_vl * L);     // X_{i-1} (absent for i == 0: never read)
+      b1[2 * i] = -(p.inv_vl * q);  b2[2 * i] = 0.0;
+      d[2 * i + 1] = s + p.inv_vg * (G + q);
+      a1[2 * i + 1] = -(p.inv_vg * p.kla_vl);  a2[2 * i + 1] = 0.0;
+      b1[2 * i + 1] = 0.0;  b2[2 * i + 1] = -(p.inv_vg * G);   // Y_{i+1} (absent for the last stage: never read)
+    }
+#pragma unroll
+    for (int k = 0; k < NX; ++k) {
+      w.ip[k] = rcp_nr(d[k]);
+      w.u1[k] = b1[k];
+      w.u2[k] = b2[k];
+      if (k + 1 < NX) {
+        const double m = a1[k + 1] * w.ip[k];
+        w.l1[k + 1] = m;
+        d[k + 1] = fma(-m, b1[k], d[k + 1]);
+        b1[k + 1] = fma(-m, b2[k], b1[k + 1]);
+      }
+      if (k + 2 < NX) {
+        const double m = a2[k + 2] * w.ip[k];
+        w.l2[k + 2] = m;
+        a1[k + 2] = fma(-m, b1[k], a1[k + 2]);
+        d[k + 2] = fma(-m, b2[k], d[k + 2]);
+      }
+    }
+  }
+  PCG_DEV static void solve(const Lin& w, double* b) {
+#pragma unroll
+    for (int i = 1; i < NX; ++i) {
+      double v = fma(-w.l1[i], b[i - 1], b[i]);
+      if (i >= 2) v = fma(-w.l2[i], b[i - 2], v);
+      b[i] = v;
+    }
+#pragma unroll
+    for (int i = NX - 1; i >= 0; --i) {
+      double v = b[i];
+      if (i + 1 < NX) v = fma(-w.u1[i], b[i + 1], v);
+      if (i + 2 < NX) v = fma(-w.u2[i], b[i + 2], v);
+      b[i] = v * w.ip[i];
+    }
+  }
 };
+using Extraction = ExtractionT<5>;
+using Extraction10 = ExtractionT<10>;
 
 // ---------------------------------------------------------------------------------------
 // four_tank -- model_classes.py:864-931

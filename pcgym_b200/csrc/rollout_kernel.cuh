@@ -257,6 +257,85 @@ PCG_DEV void advance_adaptive_aux(const Derived<M, TB>& dv, const typename M::P&
   h_carry = h;
 }
 
+// ------------------------------------------------------------------ stiff adaptive step, one environment
+// Rosenbrock method TB (RODAS4: tableaus.cuh) with the model's analytic Jacobian and its own linear solver
+// (M::factor / M::solve), one Jacobian + factorisation per attempted step, six right-hand sides and six solves.
+// Same contract as advance_adaptive: per-lane step control on err = RMS(U_6 / (atol + rtol max(|x|,|x'|))), the embedded
+// solution is one order lower so h *= clamp(0.9 err^-1/4, 0.2, 6); step carried across intervals; status bits on a
+// step-cap or a step that shrinks to nothing.  The stiff counterpart of the reference's CVODES BDF (integrator.py:163-182).
+template <class M, class TB>
+PCG_DEV void advance_rosenbrock(const typename M::P& mp, double (&x)[M::NX], const double (&u)[M::NU + M::ND], double dt,
+                                double rtol, double atol, int max_steps, double& h_carry, int& n_rhs, unsigned& status) {
+  constexpr int NX = M::NX, S = TB::S;
+  typename M::Aux aux;
+  M::prep(mp, u, aux);
+  double t = 0.0;
+  double h = (h_carry > 0.0 && h_carry < dt) ? h_carry : 0.25 * dt;
+  int steps = 0;
+  bool rejected = false;
+#pragma unroll 1
+  while (t < dt) {
+    if (steps >= max_steps) { status |= PCG_ST_STEPCAP; break; }
+    ++steps;
+    const double left = dt - t;
+    const bool last = (h >= left * (1.0 - 1e-12));
+    const double hh = last ? left : h;
+    const double inv_h = 1.0 / hh;
+    typename M::Lin w;
+    M::factor(mp, aux, x, u, inv_h * (1.0 / TB::gamma), w);
+    double U[S][NX], yi[NX];
+#pragma unroll
+    for (int i = 0; i < S; ++i) {
+#pragma unroll
+      for (int n = 0; n < NX; ++n) {
+        double acc = x[n];
+#pragma unroll
+        for (int j = 0; j < i; ++j)
+          if (TB::a(i, j) != 0.0) acc = fma(TB::a(i, j), U[j][n], acc);
+        yi[n] = acc;
+      }
+      double f[NX];
+      M::rhs(mp, aux, yi, u, f);
+#pragma unroll
+      for (int n = 0; n < NX; ++n) {
+        double acc = 0.0;
+#pragma unroll
+        for (int j = 0; j < i; ++j)
+          if (TB::c(i, j) != 0.0) acc = fma(TB::c(i, j), U[j][n], acc);
+        f[n] = fma(acc, inv_h, f[n]);
+      }
+      M::solve(w, f);
+#pragma unroll
+      for (int n = 0; n < NX; ++n) U[i][n] = f[n];
+    }
+    n_rhs += S + 1;                                  // six right-hand sides and the Jacobian
+    double sq = 0.0, xn[NX];
+#pragma unroll
+    for (int n = 0; n < NX; ++n) {
+      xn[n] = yi[n] + U[S - 1][n];                   // yi is the argument of the last stage = the embedded solution
+      const double sc = fma(rtol, fmax(fabs(x[n]), fabs(xn[n])), atol);
+      const double r = U[S - 1][n] * rcp_nr(sc);
+      sq = fma(r, r, sq);
+    }
+    const double msq = sq * (1.0 / NX);              // err^2
+    const bool finite = isfinite(msq);
+    const float grow = finite ? 0.9f * __powf(fmaxf(static_cast<float>(msq), 1e-30f), -0.125f) : 0.2f;
+    if (finite && msq <= 1.0) {
+      t = last ? dt : t + hh;
+#pragma unroll
+      for (int n = 0; n < NX; ++n) x[n] = xn[n];
+      const double hn = hh * static_cast<double>(fminf(rejected ? 1.0f : 6.0f, grow));
+      h = last ? fmax(h, hn) : hn;
+      rejected = false;
+    } else {
+      h = hh * static_cast<double>(fmaxf(0.2f, fminf(grow, 1.0f)));
+      rejected = true;
+      if (!(h > 1e-14 * dt)) { status |= PCG_ST_NONFINITE; break; }
+    }
+  }
+  h_carry = h;
+}
+
 // ------------------------------------------------------------------ the kernel
 template <class M, class TB, bool ADAPTIVE, bool GENERAL, int EPT>
 __global__ void __launch_bounds__(kBlock, (EPT == 1 && !ADAPTIVE) ? M::MIN_BLOCKS_EPT1 : M::MIN_BLOCKS)
@@ -558,9 +637,14 @@ rollout_kernel(const __grid_constant__ pcg_desc d, const __grid_constant__ pcg_i
     if constexpr (ADAPTIVE && TB::EMBEDDED) {
       draw();
 #pragma unroll
-      for (int e = 0; e < EPT; ++e)
-        advance_adaptive<M, TB>(dv, GENERAL ? p_env[e % NPL] : dv.p, x[e], uk[e], d.dt, d.rtol, d.atol, d.max_steps,
-                                h_carry[e], n_rhs[e], status[e]);
+      for (int e = 0; e < EPT; ++e) {
+        if constexpr (is_rosenbrock<TB>::value)
+          advance_rosenbrock<M, TB>(GENERAL ? p_env[e % NPL] : dv.p, x[e], uk[e], d.dt, d.rtol, d.atol, d.max_steps,
+                                    h_carry[e], n_rhs[e], status[e]);
+        else
+          advance_adaptive<M, TB>(dv, GENERAL ? p_env[e % NPL] : dv.p, x[e], uk[e], d.dt, d.rtol, d.atol, d.max_steps,
+                                  h_carry[e], n_rhs[e], status[e]);
+      }
     } else {
       typename M::Aux aux[EPT];
 #pragma unroll

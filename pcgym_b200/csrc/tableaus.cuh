@@ -74,4 +74,49 @@ struct Tsit5 {
   }
 };
 
+// RODAS4 (Hairer & Wanner, Solving ODEs II, sec. IV.7 / rodas.f): six-stage stiffly accurate, L-stable Rosenbrock
+// method of order 4 with an embedded third-order solution, in the transformed form that needs no matrix-vector
+// product with the Jacobian:
+//     W = I / (gamma h) - J(y0)
+//     W U_i = f(y0 + sum_{j<i} a(i,j) U_j) + sum_{j<i} (c(i,j) / h) U_j,      i = 1..6
+//     y1 = y0 + sum_{j<5} a(5,j) U_j + U_6          (a(5, .) = a(4, .) with a(5,4) = 1),     err = U_6
+// The stiff counterpart of the explicit pairs: the reference integrates every model with CVODES' BDF
+// (integrator.py:163-182), which follows a stiff transient (an ignited cstr, a fast extraction column) that no explicit
+// pair can.  tests/test_tableaus.py checks the coefficients through the convergence order on a stiff nonlinear problem.
+struct Rodas4 {
+  static constexpr int S = 6;
+  static constexpr bool EMBEDDED = true;
+  static constexpr bool ROSENBROCK = true;
+  static constexpr double gamma = 0.25;
+  PCG_CX double a(int i, int j) {
+    constexpr double A[7][6] = {
+        {0, 0, 0, 0, 0, 0},
+        {0.1544e1, 0, 0, 0, 0, 0},
+        {0.9466785280815826, 0.2557011698983284, 0, 0, 0, 0},
+        {0.3314825187068521e1, 0.2896124015972201e1, 0.9986419139977817, 0, 0, 0},
+        {0.1221224509226641e1, 0.6019134481288629e1, 0.1253708332932087e2, -0.6878860361058950, 0, 0},
+        {0.1221224509226641e1, 0.6019134481288629e1, 0.1253708332932087e2, -0.6878860361058950, 1.0, 0},
+        {0, 0, 0, 0, 0, 0}};
+    return A[i][j];
+  }
+  PCG_CX double c(int i, int j) {
+    constexpr double C[6][6] = {
+        {0, 0, 0, 0, 0, 0},
+        {-0.56688e1, 0, 0, 0, 0, 0},
+        {-0.2430093356833875e1, -0.2063599157091915, 0, 0, 0, 0},
+        {-0.1073529058151375, -0.9594562251023355e1, -0.2047028614809616e2, 0, 0, 0},
+        {0.7496443313967647e1, -0.1024680431464352e2, -0.3399990352819905e2, 0.1170890893206160e2, 0, 0},
+        {0.8083246795921522e1, -0.7981132988064893e1, -0.3152159432874371e2, 0.1631930543123136e2, -0.6058818238834054e1, 0}};
+    return C[i][j];
+  }
+  PCG_CX double b(int) { return 0.0; }      // the solution is formed from the stage values (see above)
+  PCG_CX double e(int) { return 0.0; }
+};
+
+// explicit tableaus have no ROSENBROCK member
+template <class TB, class = void>
+struct is_rosenbrock { static constexpr bool value = false; };
+template <class TB>
+struct is_rosenbrock<TB, decltype(void(TB::ROSENBROCK))> { static constexpr bool value = true; };
+
 }  // namespace pcg

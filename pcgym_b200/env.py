@@ -14,8 +14,8 @@ file parses the configuration into a `pcg_desc`, owns the device tensors (struct
 [field][env], fp64) and mirrors the reference's bookkeeping.  There is no CPU fallback.
 
 New optional keys: `n_envs`, `device`, `seed`, `env_id0`, `noise_mode` ("philox" | "philox_f32" |
-"external"), `integrator` = {"scheme": "tsit5"|"dopri5"|"rk4", "adaptive": bool, "rtol", "atol",
-"n_sub", "max_steps"}, `constraint_units` ("reference" | "physical"), per-env `x0` [n_envs, Nx],
+"external"), `integrator` = {"scheme": "tsit5"|"dopri5"|"rk4"|"rodas4" (stiff: Rosenbrock 4(3) with the model's
+analytic Jacobian, cstr and multistage_extraction), "adaptive": bool, "rtol", "atol", "n_sub", "max_steps"}, `constraint_units` ("reference" | "physical"), per-env `x0` [n_envs, Nx],
 per-env `SP[k]` / `disturbances[k]` [n_envs, N]; per-env model parameters that reach the DYNAMICS (an
 extension: the reference's sampled parameters only reach the observation): `model_params` =
 {"k0": array[n_envs], ...} and/or `uncertainty_in_dynamics=True`, which feeds the values reset() samples for
@@ -121,6 +121,8 @@ class make_env:
             raise ValueError(f"unknown integrator scheme {integ['scheme']!r}")
         if integ["scheme"] == "rk4":
             integ["adaptive"] = False
+        if integ["scheme"] == "rodas4":               # Rosenbrock 4(3): always step-size controlled
+            integ["adaptive"] = True
         self.integrator = integ
 
         # pcgym.py:127-158
@@ -134,6 +136,9 @@ class make_env:
                 raise ValueError("custom (affine) models run with the 'tsit5' integrator scheme")
         else:
             self.model = self._dmodel = _models.get(P.get("model"), self.integration_method)
+        if self.integrator["scheme"] == "rodas4" and not nat.lib().pcg_model_stiff_capable(self._dmodel.model_id):
+            raise ValueError(f"integrator scheme 'rodas4' needs the model's analytic Jacobian: available for 'cstr' and "
+                             f"'multistage_extraction', not for '{self._dmodel.name}'")
         minfo = self.model.info()
 
         # pcgym.py:160-165

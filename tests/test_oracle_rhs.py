@@ -55,4 +55,26 @@ def test_registry_is_complete():
             "cstr_series_recycle", "distillation_column", "multistage_extraction_reactive", "four_tank",
             "heat_exchanger", "biofilm_reactor", "polymerisation_reactor", "photobioreactor", "crystallization",
             "invariant_batch", "batch", "coupled_oscillator", "disease", "hydraulic_tank"]
-    assert sorted(keys) == sorted(orhs.RHS) == sorted(orhs.MODELS)
+    extension = ["multistage_extraction_10stage"]          # not a reference model: see test below
+    assert sorted(keys + extension) == sorted(orhs.RHS) == sorted(orhs.MODELS)
+
+
+def test_ten_stage_extension_shares_the_five_stage_balances():
+    """The ten-stage column is an EXTENSION (BASELINE config 4's wording; no reference model of that size).  What pins
+    it: (a) it runs the very code path that the reference-pinned five-stage RHS runs; (b) a ten-stage column whose
+    stages 6..10 sit exactly at the gas-feed equilibrium hands stage 5 the same inlet the five-stage column gets, so its
+    first ten derivatives equal the five-stage RHS; (c) the column's overall mass balance,
+    sum_i (Vl dX_i + Vg dY_i) = L (X0 - X_N) + G (Y_{N+1} - Y_1), for random states."""
+    rng = np.random.default_rng(0)
+    p5, p10 = orhs.default_params("multistage_extraction"), orhs.default_params("multistage_extraction_10stage")
+    u = np.array([120.0, 300.0])
+    x5 = rng.uniform(0.05, 0.6, 10)
+    x10 = np.concatenate([x5, np.tile([0.0, p5["Y6"]], 5)])     # Y6..Y10 = the five-stage gas feed
+    d5 = orhs.rhs("multistage_extraction", x5, u)
+    d10 = orhs.rhs("multistage_extraction_10stage", x10, u)
+    np.testing.assert_allclose(d10[:10], d5, rtol=1e-14, atol=1e-15)
+    for name, p, n, yfeed in (("multistage_extraction", p5, 5, p5["Y6"]), ("multistage_extraction_10stage", p10, 10, p10["Y11"])):
+        x = rng.uniform(0.05, 0.6, 2 * n)
+        d = orhs.rhs(name, x, u)
+        total = p["Vl"] * d[0::2].sum() + p["Vg"] * d[1::2].sum()
+        np.testing.assert_allclose(total, u[0] * (p["X0"] - x[2 * n - 2]) + u[1] * (yfeed - x[1]), rtol=1e-12)

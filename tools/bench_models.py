@@ -36,6 +36,14 @@ CONFIGS = [   # model, n_envs, K, integrator[, measurement noise (default on)]
     ("crystallization", 65536, 19, {"scheme": "tsit5", "adaptive": False, "n_sub": 8}),   # random inputs diverge the moments after ~24 intervals (oracle too)
     ("biofilm_reactor", 32768, 19, {"scheme": "tsit5", "adaptive": True, "rtol": 1e-8, "atol": 1e-10}),
     ("multistage_extraction", 32768, 59, {"scheme": "tsit5", "adaptive": True, "rtol": 1e-8, "atol": 1e-10}),
+    # the stiff integrator (Rosenbrock RODAS4, analytic Jacobian) on the same two workloads, same tolerances
+    ("multistage_extraction", 32768, 59, {"scheme": "rodas4", "rtol": 1e-8, "atol": 1e-10}),
+    ("cstr", 65536, 99, {"scheme": "rodas4", "rtol": 1e-8, "atol": 1e-8}),
+    ("multistage_extraction", 32768, 59, {"scheme": "rodas4", "rtol": 1e-6, "atol": 1e-9}),
+    ("multistage_extraction", 32768, 59, {"scheme": "tsit5", "adaptive": True, "rtol": 1e-6, "atol": 1e-9}),
+    # BASELINE config 4 as worded ("10-stage, ~20-state"): the labelled extension model
+    ("multistage_extraction_10stage", 32768, 59, {"scheme": "tsit5", "adaptive": True, "rtol": 1e-8, "atol": 1e-10}),
+    ("multistage_extraction_10stage", 32768, 59, {"scheme": "rodas4", "rtol": 1e-8, "atol": 1e-10}),
 ]
 
 
@@ -51,7 +59,7 @@ def main():
     ap.add_argument("--config", type=int, default=0, help="BASELINE config 2 (first_order) or 4 (extraction): only those rows")
     ap.add_argument("--only", default="", help="comma-separated indices into CONFIGS (ncu captures of one kernel family)")
     args = ap.parse_args()
-    only = {int(v) for v in args.only.split(",") if v != ""} or {2: {0, 1}, 4: {10}}.get(args.config, set())
+    only = {int(v) for v in args.only.split(",") if v != ""} or {2: {0, 1}, 4: {10, 11, 15, 16}}.get(args.config, set())
     peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(
         os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
     for idx, cfg in enumerate(CONFIGS):
