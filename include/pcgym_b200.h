@@ -14,7 +14,7 @@
  *   - work is enqueued on `cuda_stream` (a cudaStream_t, NULL = legacy default
  *     stream) and the call returns without synchronising;
  *   - numerical trouble is reported per environment in `io.status`
- *     (bit0 non-finite state, bit1 adaptive step cap hit), never as a host error;
+ *     (bit0 non-finite state, bit1 adaptive step cap hit, bit2 out of a kernel's table range), never as a host error;
  *   - no global mutable state: re-entrant across streams and threads; no
  *     allocation on the hot path.
  *   - data layout: struct-of-arrays, fp64, environment index contiguous
@@ -146,6 +146,9 @@ enum pcg_kernel {
 /* per-env status bits written to io.status */
 #define PCG_ST_NONFINITE 1
 #define PCG_ST_STEPCAP   2
+#define PCG_ST_RANGE     4   /* the state left the band a table-driven kernel covers (build option CstrW of the per-SM kernel: reactor
+                                temperature outside 250..760 K at the end of an interval); the env's results are not
+                                valid from there on -- such dynamics need scheme RODAS4 or pcg_set_kernel(PCG_KERNEL_GENERIC) */
 
 /* Host-side descriptor, passed by value to the kernel (constant bank).  Everything
  * the reference keeps on the make_env object that the step needs. */

@@ -138,4 +138,42 @@ PCG_DEV void exp_tab_split(double x, const double* tab, double& scale, double& p
   poly = fma(fma(fma(fma(kET.c4, r, kET.c3), r, kET.c2), r, 1.0), r, 1.0);
 }
 
+// The same exponential with the table indexed DIRECTLY by n = rint(256 x log2 e): tab[n - n_min] = 2^(n/256) for every
+// n the caller's argument range can produce (the per-SM kernel builds it in shared memory from kExp2Tab at CTA start:
+// exp_wide_fill).  `shift` = 1.5*2^52 - n_min puts n - n_min into the low word of the shifted double, so the whole
+// integer side of the evaluation is ONE unsigned clamp and the address of a shared-memory load -- exp_tab_split's
+// split / saturate / mask / exponent-add sequence (9 integer instructions per call, 54 per Tsit5 step, each an issue
+// slot of the bound resource) is gone.  Same FP64 work, same rounding (2^(n/256) is the 256-entry
+// table value with an exact power-of-two scaling).  An argument outside the table reads its first / last entry: the
+// caller flags such lanes (PCG_ST_RANGE).  NaN-propagating through `poly`.
+PCG_DEV void exp_wide_split(double x, const double* tab, double shift, unsigned last, double& scale, double& poly) {
+  const double t = fma(x, kET.l256, shift);
+  const unsigned idx = min(static_cast<unsigned>(__double2loint(t)), last);
+  const double nf = t - shift;
+  const double r = fma(nf, kET.nln2_256, x);
+  scale = tab[idx];
+  poly = fma(fma(fma(fma(kET.c4, r, kET.c3), r, kET.c2), r, 1.0), r, 1.0);
+}
+
+// whole CTA: tab[i] = 2^((i + n_min)/256), i = 0..last
+PCG_DEV void exp_wide_fill(double* tab, int n_min, int last) {
+  for (int i = threadIdx.x; i <= last; i += blockDim.x) {
+    const int n = i + n_min;
+    const double tj = kExp2Tab[n & 255];
+    tab[i] = __hiloint2double(__double2hiint(tj) + ((n >> 8) << 20), __double2loint(tj));
+  }
+}
+
+// high word of a double, host or device (positive normal doubles order like their high words)
+PCG_HD int hi_word(double v) {
+#ifdef __CUDA_ARCH__
+  return __double2hiint(v);
+#else
+  long long b;
+  static_assert(sizeof b == sizeof v, "");
+  __builtin_memcpy(&b, &v, sizeof b);
+  return static_cast<int>(b >> 32);
+#endif
+}
+
 }  // namespace pcg

@@ -167,9 +167,14 @@ inline int sm_count() {                      // of the calling thread's current 
 
 // eligible when every SM gets 2..8 tiles of 64 envs (9.5 k < n <= 75.8 k on 148 SMs) and `done` cannot depend on
 // earlier violations
+template <class M>
 inline bool wsm_ok(const pcg_desc& d, const pcg_io& io, int64_t n_env, int64_t k_steps, int64_t* envs_per_cta,
                    int* n_tiles) {
   if (d.flags & PCG_F_DONE_ON_VIOLATION) return false;
+  // the per-SM kernel's model variant may tabulate over a bounded argument range (cstr: CstrW): the parameters must fit
+  if constexpr (has_wide_tab<typename M::WsmModel>::value) {
+    if (!M::WsmModel::wide_ok(M::WsmModel::make(d.theta))) return false;
+  }
   // the finishers address with 32-bit element indices
   const int64_t lim = int64_t{1} << 31;
   if (k_steps * PCG_MAX_OBS * n_env >= lim) return false;
@@ -281,9 +286,9 @@ cudaError_t launch_e(const pcg_desc& d, const pcg_io& io, int64_t n_env, int t0,
           static const bool wsm_off = [] { const char* e = std::getenv("PCG_WSM"); return e && std::atoi(e) == 0; }();
           int64_t epc = 0;
           int tiles = 0;
-          if (two && wsm_ok(d, io, n_env, k_steps, &epc, &tiles) &&
+          if (two && wsm_ok<M>(d, io, n_env, k_steps, &epc, &tiles) &&
               (req == PCG_KERNEL_WSM || (req == PCG_KERNEL_AUTO && !wsm_off)))
-            return launch_wsm<typename M::WsModel, TB>(d, io, n_env, t0, k_steps, s, epc, tiles);
+            return launch_wsm<typename M::WsmModel, TB>(d, io, n_env, t0, k_steps, s, epc, tiles);
           const bool ws = req == PCG_KERNEL_WS || ((req == PCG_KERNEL_AUTO || req == PCG_KERNEL_WSM) && ws_preferred(n_env));
           // the integrator warps run the model's WsModel (cstr: table-driven exp, 8 FP64 issue slots fewer per RHS)
           if (two && ws) return launch_ws<typename M::WsModel, TB, 1>(d, io, n_env, t0, k_steps, s);
@@ -299,8 +304,8 @@ cudaError_t launch_e(const pcg_desc& d, const pcg_io& io, int64_t n_env, int t0,
       int64_t epc = 0;
       int tiles = 0;
       if (!generic && two && d.noise != PCG_NOISE_PHILOX_F32 && fast_ok<M>(d, io, true) &&
-          wsm_ok(d, io, n_env, k_steps, &epc, &tiles) && (req == PCG_KERNEL_WSM || req == PCG_KERNEL_AUTO))
-        return launch_wsm<typename M::WsModel, TB, true>(d, io, n_env, t0, k_steps, s, epc, tiles);
+          wsm_ok<M>(d, io, n_env, k_steps, &epc, &tiles) && (req == PCG_KERNEL_WSM || req == PCG_KERNEL_AUTO))
+        return launch_wsm<typename M::WsmModel, TB, true>(d, io, n_env, t0, k_steps, s, epc, tiles);
     }
   }
   if constexpr (!ADAPTIVE && M::EPT == 2) {

@@ -28,6 +28,9 @@ namespace pcg {
 #ifndef PCG_CSTR_WSMODEL
 #define PCG_CSTR_WSMODEL CstrT
 #endif
+#ifndef PCG_CSTR_WSMMODEL
+#define PCG_CSTR_WSMMODEL CstrT
+#endif
 struct Cstr {
   static constexpr int NX = 2, NU = 1, ND = 2, NP = 10;
   struct P { double thru, ln_k0, neg_ear, c_heat, c_cool, c_T; };
@@ -54,6 +57,7 @@ struct Cstr {
   static constexpr bool FAST = true;              // has straight-line kernel instantiations (rollout_fast / rollout_ws)
   static constexpr int WS = 1;                    // warp-specialised kernel: integrator/finisher pairs per CTA
   using WsModel = struct PCG_CSTR_WSMODEL;        // RHS variant its integrator warps run (CstrT; -DPCG_CSTR_WSMODEL=CstrH: A/B)
+  using WsmModel = struct PCG_CSTR_WSMMODEL;      // the same for the per-SM kernel (CstrT; -DPCG_CSTR_WSMMODEL=CstrW -DPCG_WSM_RING=8 -DPCG_WSM_WARPS=24: A/B)
   PCG_DEV static void rhs(const P& p, const Aux& a, const double* x, const double*, double* dx) {
     const double ca = x[0], T = x[1];
     const double rate = exp_sat(fma(p.neg_ear, rcp_nr(T), p.ln_k0)) * ca;        // :52
@@ -110,6 +114,58 @@ struct CstrT : Cstr {
     const double ca = x[0], T = x[1];
     double scale, poly;
     exp_tab_split(fma(p.neg_ear, rcp_o3(T), p.ln_k0), a.tab, scale, poly);       // :52  k0 exp(-E/RT) = scale * poly
+    const double sc = scale * ca, hs = p.c_heat * sc;
+    dx[0] = fma(-sc, poly, fma(-p.thru, ca, a.feed_c));                           // :53
+    dx[1] = fma(hs, poly, fma(p.c_T, T, a.heat0));                                // :54-58
+  }
+};
+
+// A/B variant for the per-SM kernel (rollout_wsm.cuh; build with -DPCG_CSTR_WSMMODEL=CstrW -DPCG_WSM_RING=8
+// -DPCG_WSM_WARPS=24 -DPCG_WSM_FIN_REGS=96): the Arrhenius factor k0 exp(-E/RT) comes from a shared-memory table indexed
+// DIRECTLY by n = rint(256 y log2 e), y = ln k0 - (E/R)/T, built per CTA for every n a reactor temperature in
+// [kTabLo, kTabHi] can produce (exp_wide_split: the integer side of the exponential is one clamp and one address;
+// 243 instead of 270 instructions per lane-interval).  The table has EXP_WIDE entries at most (75 KB: the rings shrink
+// to 8 slots to make room), which covers 240..800 K for the reference parameters; wide_ok() tells the launcher whether a
+// parameter set fits.  A lane whose temperature leaves [kChkLo, kChkHi] at the end of an interval is flagged
+// PCG_ST_RANGE.  MEASURED (profiles/README.md r2, same-box A/B): 0.157-0.160 ms against 0.157-0.164 ms for CstrT at
+// 65 536 envs -- no gain: at 443 envs per SM the kernel is bound by how many independent dependency chains a scheduler
+// holds, not by issue slots -- and +4 % for the adaptive scheme.  Not the default: the table narrows the valid
+// temperature range for nothing at the headline.
+struct CstrW : Cstr {
+  using WsModel = CstrW;
+  static constexpr bool EXP_TAB = true;
+  static constexpr int EXP_WIDE = 9600;
+  static constexpr double kTabLo = 240.0, kTabHi = 800.0, kChkLo = 250.0, kChkHi = 760.0;
+  struct P : Cstr::P { double wshift; int n_min, wlast, chk_hi0, chk_span; };
+  PCG_HD static P make(const double* th) {
+    P p;
+    static_cast<Cstr::P&>(p) = Cstr::make(th);
+    const double l256 = 369.3299304675746;
+    const double n_lo = floor(fma(p.neg_ear, 1.0 / kTabLo, p.ln_k0) * l256) - 2.0;
+    const double n_hi = ceil(fma(p.neg_ear, 1.0 / kTabHi, p.ln_k0) * l256) + 2.0;
+    const bool sane = n_lo > -1e6 && n_hi < 1e6 && n_hi > n_lo;      // also false for NaN parameters
+    p.n_min = sane ? static_cast<int>(n_lo) : 0;
+    p.wlast = sane ? static_cast<int>(n_hi - n_lo) : -1;
+    p.wshift = 6755399441055744.0 - static_cast<double>(p.n_min);
+    p.chk_hi0 = hi_word(kChkLo);
+    p.chk_span = hi_word(kChkHi) - p.chk_hi0;
+    return p;
+  }
+  PCG_HD static bool wide_ok(const P& p) { return p.wlast >= 1 && p.wlast < EXP_WIDE && p.neg_ear < 0.0; }
+  struct Aux { double feed_c, heat0; const double* tab; };
+  PCG_DEV static void prep(const P& p, const double* u, Aux& a) {
+    a.feed_c = p.thru * u[2];
+    a.heat0 = fma(p.thru, u[1], p.c_cool * u[0]);
+  }
+  PCG_DEV static void fill_tab(double* tab, const P& p) { exp_wide_fill(tab, p.n_min, p.wlast); }
+  // PCG_ST_RANGE when the temperature (or a NaN: high word 0x7ff8....) is outside the checked band; integer compare
+  PCG_DEV static unsigned range_flag(const P& p, const double* x) {
+    return static_cast<unsigned>(__double2hiint(x[1]) - p.chk_hi0) > static_cast<unsigned>(p.chk_span) ? 4u : 0u;
+  }
+  PCG_DEV static void rhs(const P& p, const Aux& a, const double* x, const double*, double* dx) {
+    const double ca = x[0], T = x[1];
+    double scale, poly;
+    exp_wide_split(fma(p.neg_ear, rcp_o3(T), p.ln_k0), a.tab, p.wshift, static_cast<unsigned>(p.wlast), scale, poly);   // :52
     const double sc = scale * ca, hs = p.c_heat * sc;
     dx[0] = fma(-sc, poly, fma(-p.thru, ca, a.feed_c));                           // :53
     dx[1] = fma(hs, poly, fma(p.c_T, T, a.heat0));                                // :54-58

@@ -76,11 +76,30 @@ struct uses_exp_tab : std::false_type {};
 template <class M>
 struct uses_exp_tab<M, std::enable_if_t<M::EXP_TAB>> : std::true_type {};
 
+// models whose table is indexed directly over their whole argument range (exp_wide_split): M::EXP_WIDE entries
+template <class M, class = void>
+struct has_wide_tab : std::false_type {};
 template <class M>
-PCG_DEV void fill_exp_tab(double* tab) {          // whole CTA, before the __syncthreads that publishes the barriers
-  if constexpr (uses_exp_tab<M>::value) {
+struct has_wide_tab<M, std::enable_if_t<(M::EXP_WIDE > 0)>> : std::true_type {};
+template <class M>
+constexpr int exp_tab_doubles() {
+  if constexpr (has_wide_tab<M>::value) return M::EXP_WIDE;
+  else return uses_exp_tab<M>::value ? 256 : 1;
+}
+
+template <class M>
+PCG_DEV void fill_exp_tab(double* tab, const typename M::P& p) {   // whole CTA, before the __syncthreads that publishes the barriers
+  if constexpr (has_wide_tab<M>::value) {
+    M::fill_tab(tab, p);
+  } else if constexpr (uses_exp_tab<M>::value) {
     for (int i = threadIdx.x; i < 256; i += blockDim.x) tab[i] = kExp2Tab[i];
   }
+}
+// PCG_ST_RANGE for a state outside the band a wide-table model checks at interval ends; 0 for every other model
+template <class M>
+PCG_DEV unsigned range_flag(const typename M::P& p, const double* x) {
+  if constexpr (has_wide_tab<M>::value) return M::range_flag(p, x);
+  else return 0u;
 }
 template <class M>
 PCG_DEV void bind_exp_tab(typename M::Aux& a, const double* tab) {
@@ -102,9 +121,9 @@ ws_rollout_kernel(const __grid_constant__ pcg_desc d, const __grid_constant__ pc
                   const __grid_constant__ Derived<M, TB> dv, const int64_t n, const int t0, const int k_steps) {
   constexpr int NX = M::NX, NU = M::NU, ND = M::ND, NUK = NU + ND, EPT = 2, R = kWsRing;
   __shared__ __align__(16) WsPair<M> sm[W];
-  __shared__ double exp_tab[uses_exp_tab<M>::value ? 256 : 1];
+  __shared__ double exp_tab[exp_tab_doubles<M>()];
   __shared__ __align__(16) double icdf_s[NOISE == PCG_NOISE_PHILOX ? kIcdfDoubles : 2];
-  fill_exp_tab<M>(exp_tab);
+  fill_exp_tab<M>(exp_tab, dv.p);
   if constexpr (NOISE == PCG_NOISE_PHILOX) fill_icdf_tab(icdf_s);
   // Role placement.  A warp's scheduler (SM sub-partition) is its hardware slot %warpid mod 4 and the CTAs of an
   // SM occupy consecutive slots, so a fixed (integrator, finisher) order would put every integrator warp -- the

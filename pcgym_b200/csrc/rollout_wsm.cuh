@@ -43,6 +43,9 @@ namespace pcg {
 #ifndef PCG_WSM_FIN_REGS
 #define PCG_WSM_FIN_REGS 88
 #endif
+#ifndef PCG_WSM_RING
+#define PCG_WSM_RING 16            // ring slots per tile (8 makes room for CstrW's direct exponential table: A/B)
+#endif
 #ifndef PCG_WSM_PREFETCH
 #define PCG_WSM_PREFETCH 1         // take the next task id while the current task runs (hides the shared-memory atomic)
 #endif
@@ -58,11 +61,12 @@ constexpr int kWsmMaxTiles = 8;    // 64-env tiles per CTA (<= 512 envs per SM)
 static_assert(kWsmIntClass == 0 || kWsmIntClass >= kWsmMaxTiles * kWsmIpt, "integrator class must hold every integrator warp");
 // Ring depth.  An mbarrier wait names its phase by PARITY only, so a waiter may never be a whole phase ahead of the
 // barrier.  A finisher holding interval k + RING of a tile while interval k of the same tile is still waiting for the
-// integrator would be exactly that; all the intervals in between would be outstanding too, i.e. RING + 1 finishers
-// stuck on one tile.  With RING >= the number of finishers (capped at kWsmMaxFin) that cannot happen, so no further
-// ordering is needed between finishers (an earlier version with RING = 8 had to serialise tasks per slot with a counter).
-constexpr int kWsmRing = 16;
-constexpr int kWsmMaxFin = 16;
+// integrator would be exactly that.  The task loop rules it out with a gate on full_a (see there): a finisher looks at
+// full_x[s] for interval k only after task (p, k - RING) has completed.  The gate's own wait is exact while a tile has
+// at most 2 RING tasks outstanding, which RING >= the number of finishers (capped at kWsmMaxFin; each owns its current
+// and its prefetched task) guarantees.
+constexpr int kWsmRing = PCG_WSM_RING;
+constexpr int kWsmMaxFin = PCG_WSM_RING;
 static_assert(kWsmRing >= kWsmMaxFin && (kWsmRing & (kWsmRing - 1)) == 0, "ring depth vs finisher count");
 
 // ADAPT = the integrator warps run the embedded pair with per-lane step-size control (advance_adaptive_aux: make_env's
@@ -99,7 +103,7 @@ struct WsmShared {
   WsPair<M, kWsmRing> tile[kWsmMaxTiles];
   uchar2 done0[kWsmMaxTiles][32];   // sticky done flag each env entered the launch with
   int next_task;
-  double exp_tab[uses_exp_tab<M>::value ? 256 : 1];   // 2^(j/256) for exp_tab_split (integrator warps)
+  double exp_tab[exp_tab_doubles<M>()];               // 2^(j/256) for exp_tab_split, or the direct table of exp_wide_split (integrator warps)
   alignas(16) double icdf[NOISE == PCG_NOISE_PHILOX ? kIcdfDoubles : 2];   // kIcdfTab (finishers; read as double2)
   double sp[SPS ? NSP : 1][SPS ? kWsmSpMax : 1];      // SP[j][t0 + i], i = 0..k_steps
 };
@@ -137,7 +141,7 @@ wsm_rollout_kernel(const __grid_constant__ pcg_desc d, const __grid_constant__ p
     }
   }
   if (threadIdx.x == 0) sh.next_task = 0;
-  fill_exp_tab<M>(sh.exp_tab);
+  fill_exp_tab<M>(sh.exp_tab, dv.p);
   if constexpr (NOISE == PCG_NOISE_PHILOX) {
     fill_icdf_tab(sh.icdf);
   }
@@ -184,6 +188,7 @@ wsm_rollout_kernel(const __grid_constant__ pcg_desc d, const __grid_constant__ p
     double h_carry = (ADAPT && io.h_carry) ? io.h_carry[env0] : 0.0;
     int n_rhs = 0;
     unsigned st_adapt = 0;
+    unsigned st_range[EPI] = {};
     // the finishers read the initial state for the t == 0 pre-check before they release interval 0, so io.x may be
     // overwritten at the end without a race
 #pragma unroll 1
@@ -215,10 +220,12 @@ wsm_rollout_kernel(const __grid_constant__ pcg_desc d, const __grid_constant__ p
 #pragma unroll
         for (int e = 0; e < EPI; ++e) reinterpret_cast<double*>(&sp.x[s][i][lane])[h + e] = x[e][i];
       mbar_arrive(&sp.full_x[s]);
+#pragma unroll
+      for (int e = 0; e < EPI; ++e) st_range[e] |= range_flag<M>(dv.p, x[e]);  // wide-table models: state left the table's band
     }
 #pragma unroll
     for (int e = 0; e < EPI; ++e) {
-      unsigned status = st_adapt;
+      unsigned status = st_adapt | st_range[e];
 #pragma unroll
       for (int i = 0; i < NX; ++i) {
         if (!isfinite(x[e][i])) status |= PCG_ST_NONFINITE;
@@ -379,6 +386,14 @@ wsm_rollout_kernel(const __grid_constant__ pcg_desc d, const __grid_constant__ p
       }
     }
     const int c = k / R;
+    // Gate: slot s may only be waited on once task (p, k - R) has completed, i.e. once ITS prefetch of this interval's
+    // action rows has landed (phase c of full_a[s]).  Without it a finisher could reach interval k while interval k - R
+    // of the same tile is still outstanding -- a finisher owns its current AND its prefetched task, so R + 1 outstanding
+    // tasks of one tile need only (R + 1) / 2 finishers when that tile's integrators lag (two integrator warps on one
+    // scheduler against one for another tile) -- and full_x[s], still a whole phase behind, would let the parity-only
+    // wait below pass at once (measured: 20 000 envs = 3 tiles per SM hung with the 8-slot ring).  The gate itself is
+    // exact as long as fewer than 2 R + 1 tasks of a tile are owned at a time: n_fin <= R finishers own at most 2 R.
+    if (k >= R) mbar_wait_backoff(&sp.full_a[s], c & 1);
     mbar_wait_backoff(&sp.full_x[s], c & 1);
     // (written in the prologue before the tile's ring was released: ordered by the full_a -> full_x chain)
     const uchar2 d0 = sh.done0[p][lane];

@@ -487,6 +487,40 @@ def test_every_straight_line_kernel_against_the_oracle_same_scheme(model, n, req
     assert out["done"][-1].all() and not out["done"][:-1].any()
 
 
+@pytest.mark.parametrize("tiles", [2, 3, 4, 5, 6, 7, 8])
+def test_per_sm_kernel_every_tile_count_long_horizon(tiles):
+    """The per-SM kernel at every tile count it accepts (2..8 tiles of 64 envs per SM), last tile partial, over a horizon
+    that wraps its 8-slot rings a dozen times.  With few tiles per SM the integrator warps of different tiles share the
+    four schedulers unevenly (3 tiles: 2 + 2 + 1 + 1 warps) and drift apart by a ring's depth -- the regime where a
+    parity-only mbarrier wait a whole phase ahead stalled the kernel before the full_a gate (csrc/rollout_wsm.cuh).
+    Same integrator arithmetic as the pair-per-CTA kernel up to the exponential's table form: states to 2e-12, and the
+    run must terminate."""
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    n = 2 * ((sms * (64 * tiles - 10)) // 2)
+    params = cases.cstr_dist_cons()
+    params.pop("disturbances"); params.pop("disturbance_bounds")
+    N = 100
+    params.update(noise=True, noise_percentage=0.001, integrator=HEADLINE, seed=5, N=N, tsim=N * 0.25,
+                  SP={"Ca": [0.85] * (N // 2) + [0.9] * (N - N // 2)})
+    rng = np.random.default_rng(tiles)
+    acts = torch.as_tensor(rng.uniform(-1, 1, (N - 1, 1, n))).cuda()
+    outs = []
+    for req, want in (("wsm", "wsm_rollout_kernel"), ("fast", "fast_rollout_kernel")):
+        with forced_kernel(req) as fk:
+            env = _env(params, n_envs=n)
+            env.reset()
+            out = env.rollout(acts)
+            torch.cuda.synchronize()
+            assert fk.last().startswith(want), (tiles, n, fk.last())
+            assert int(env.status.max()) == 0
+            outs.append({k: out[k].clone() for k in ("x", "obs", "reward", "done", "violated")})
+    a, b = outs
+    assert rel(a["x"].cpu().numpy(), b["x"].cpu().numpy()) < 2e-12
+    np.testing.assert_allclose(a["obs"].cpu().numpy(), b["obs"].cpu().numpy(), rtol=0, atol=1e-10)
+    assert torch.equal(a["done"], b["done"])
+    assert (a["violated"] == b["violated"]).double().mean() > 0.9999
+
+
 @pytest.mark.parametrize("n", [65536, 20000])
 def test_default_adaptive_scheme_in_the_per_sm_kernel(n):
     """make_env's DEFAULT integrator (adaptive Tsit5, rtol = atol = 1e-8, the reference's jax path integrator.py:65-88)

@@ -8,4 +8,4 @@ mkdir -p ../../ab build_$NAME
 for o in build/*.o; do b=$(basename $o); [ "$b" = inst_cstr.o ] || cp -u $o build_$NAME/$b; done
 touch -c build_$NAME/*.o
 make -s OUT=../../ab/lib_$NAME.so BUILD=build_$NAME EXTRA="$EXTRA" -j8
-grep -A2 "wsm_rollout_kernelINS_5CstrTENS_5Tsit5ELi1ELi1ELb0ELb1E" build_$NAME/inst_cstr.ptxas.log | grep -E "registers|spill" | head -4
+grep -A2 "wsm_rollout_kernelINS_5CstrWENS_5Tsit5ELi1ELi1ELb0ELb1ELb0E" build_$NAME/inst_cstr.ptxas.log | grep -E "registers|spill" | head -4
