@@ -165,8 +165,8 @@ inline int sm_count() {                      // of the calling thread's current 
   return v;
 }
 
-// eligible when every SM gets 2..8 tiles of 64 envs (9.5 k < n <= 75.8 k on 148 SMs) and `done` cannot depend on
-// earlier violations
+// eligible when every CTA gets 2..8 tiles of 64 envs (n > 9.5 k on 148 SMs) and `done` cannot depend on earlier
+// violations
 template <class M>
 inline bool wsm_ok(const pcg_desc& d, const pcg_io& io, int64_t n_env, int64_t k_steps, int64_t* envs_per_cta,
                    int* n_tiles) {
@@ -180,8 +180,12 @@ inline bool wsm_ok(const pcg_desc& d, const pcg_io& io, int64_t n_env, int64_t k
   if (k_steps * PCG_MAX_OBS * n_env >= lim) return false;
   if (io.sp_st < 0 || io.sp_sj < 0 || io.sp_se < 0 ||
       (d.N + 1) * io.sp_st + PCG_MAX_NSP * io.sp_sj + (n_env + 2) * io.sp_se >= lim) return false;
+  // One CTA per SM and wave: batches beyond 8 tiles per SM run as several waves of CTAs (one resident per SM, the
+  // hardware starts the next as one retires), each again a 2..8-tile rollout of its own envs over all k_steps.
   const int64_t sms = sm_count();
-  const int64_t epc = 2 * ((n_env + 2 * sms - 1) / (2 * sms));
+  const int64_t waves = (n_env + sms * 64 * kWsmMaxTiles - 1) / (sms * 64 * kWsmMaxTiles);
+  const int64_t ctas = sms * waves;
+  const int64_t epc = 2 * ((n_env + 2 * ctas - 1) / (2 * ctas));
   const int tiles = static_cast<int>((epc + 63) / 64);
   *envs_per_cta = epc;
   *n_tiles = tiles;

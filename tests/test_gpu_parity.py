@@ -143,8 +143,8 @@ def test_rollout_host_selected_outputs():
     assert same(ref["obs"], keep)
 
 
-@pytest.mark.parametrize("n", [4096, 20000, 78000])        # pair-per-CTA, per-SM finisher pool (partial CTA), monolithic
-def test_split_rollouts_equal_one_rollout_bitwise(n):
+@pytest.mark.parametrize("n,request_", [(4096, "auto"), (20000, "auto"), (78000, "fast"), (78000, "auto")])
+def test_split_rollouts_equal_one_rollout_bitwise(n, request_):     # pair-per-CTA, per-SM pool (partial CTA), monolithic, per-SM pool in two waves
     """A K-interval rollout cut at arbitrary points (1, 2, 5, 8, 9 intervals: below / at / above the ring depth of the
     warp-specialised kernels, t0 > 0) reproduces the single launch bit for bit, including the sticky done flag and
     cons_info rows."""
@@ -156,13 +156,14 @@ def test_split_rollouts_equal_one_rollout_bitwise(n):
     acts = torch.as_tensor(rng.uniform(-1, 1, (K, 1, n))).cuda()
     one, many = _env(params, n_envs=n), _env(params, n_envs=n)
     one.reset(); many.reset()
-    ref = one.rollout(acts)
-    cuts, k0 = [1, 2, 5, 8, 9], 0
-    parts = []
-    for c in cuts + [K - sum(cuts)]:
-        out = many.rollout(acts[k0:k0 + c])
-        parts.append({k: v.clone() for k, v in out.items() if v is not None})
-        k0 += c
+    with forced_kernel(request_):
+        ref = one.rollout(acts)
+        cuts, k0 = [1, 2, 5, 8, 9], 0
+        parts = []
+        for c in cuts + [K - sum(cuts)]:
+            out = many.rollout(acts[k0:k0 + c])
+            parts.append({k: v.clone() for k, v in out.items() if v is not None})
+            k0 += c
     for key in ("x", "obs", "reward", "done", "violated"):
         assert same(torch.cat([p[key] for p in parts]).double(), ref[key].double()), key
     assert same(one.info["cons_info"], many.info["cons_info"]) and same(one._x, many._x)
@@ -183,14 +184,16 @@ def test_three_straight_line_kernels_agree():
     x0 = np.array([0.8, 330.0, 0.8])[None] * (1 + 0.02 * rng.uniform(-1, 1, (78000, 3)))
     acts = rng.uniform(-1, 1, (K, 1, 78000))
     outs, kernels = [], []
-    for n in (4096, 20000, 78000):
+    for n, req in ((4096, "auto"), (20000, "auto"), (78000, "fast"), (78000, "auto")):
         env = _env(dict(params, x0=x0[:n]), n_envs=n)
         env.reset()
-        out = env.rollout(torch.as_tensor(acts[:, :, :n].copy()))
+        with forced_kernel(req):
+            out = env.rollout(torch.as_tensor(acts[:, :, :n].copy()))
         kernels.append(nat.lib().pcg_last_kernel().decode().split(" ")[0])
         outs.append({k: out[k][..., :m].cpu().numpy().astype(np.float64) for k in ("x", "obs", "reward", "done", "violated")})
         assert int(env.status.max()) == 0
-    assert kernels == ["ws_rollout_kernel", "wsm_rollout_kernel", "fast_rollout_kernel"], kernels
+    # 78 000 envs are more than 8 tiles per SM: the library runs the per-SM kernel in two waves of CTAs
+    assert kernels == ["ws_rollout_kernel", "wsm_rollout_kernel", "fast_rollout_kernel", "wsm_rollout_kernel"], kernels
     for other in outs[1:]:
         np.testing.assert_allclose(other["x"], outs[0]["x"], rtol=2e-12, atol=0)
         np.testing.assert_allclose(other["obs"], outs[0]["obs"], rtol=0, atol=1e-10)
@@ -199,6 +202,7 @@ def test_three_straight_line_kernels_agree():
         np.testing.assert_allclose(other["reward"][ok], outs[0]["reward"][ok], rtol=1e-9, atol=1e-12)
         assert np.array_equal(other["done"], outs[0]["done"])
     assert np.array_equal(outs[1]["x"], outs[0]["x"])             # same integrator code in both warp-specialised kernels
+    assert np.array_equal(outs[3]["x"], outs[0]["x"])
 
 
 # ----------------------------------------------------------------------------- golden do-mpc trajectories through CUDA
