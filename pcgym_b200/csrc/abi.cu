@@ -141,7 +141,8 @@ int validate(const pcg_desc* d, const pcg_io* io, int64_t n_env, int64_t t0, int
   const bool adaptive = (d->flags & PCG_F_ADAPTIVE) != 0;
   if (adaptive && d->scheme == PCG_SCHEME_RK4) return PCG_E_SCHEME;
   if (d->scheme == PCG_SCHEME_RODAS4 && (!adaptive || !kModels[d->model].stiff)) return PCG_E_SCHEME;   // adaptive, Jacobian needed
-  if (d->model >= PCG_MODEL_AFFINE_BASE && d->scheme != PCG_SCHEME_TSIT5) return PCG_E_SCHEME;   // Tsit5 kernels only
+  if (d->model >= PCG_MODEL_AFFINE_BASE && d->model < PCG_MODEL_EXTRACTION_10 && d->scheme != PCG_SCHEME_TSIT5)
+    return PCG_E_SCHEME;                                       // the affine custom models have Tsit5 kernels only
   const ModelInfo& m = kModels[d->model];
   if (d->nu_a != m.nu) return PCG_E_DIMS;
   if (d->model == PCG_MODEL_OSCILLATORS && d->theta[0] != pcg::Oscillators::NOSC) return PCG_E_DIMS;   // state count is 2 N

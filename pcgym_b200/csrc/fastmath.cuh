@@ -164,6 +164,49 @@ PCG_DEV void exp_wide_fill(double* tab, int n_min, int last) {
   }
 }
 
+// sqrt(a) for the right-hand sides (four_tank: four per evaluation; the CUDA library's sqrt carries a slow-path branch
+// that splits the basic block, 30 instructions each): MUFU.RSQ64H seed (2^-22), one coupled Goldschmidt step for
+// (sqrt a, 1 / (2 sqrt a)) and a final residual correction -- 7 FP64 instructions, <= 1 ulp.  a < 0 and NaN give NaN like
+// the reference's np.sqrt; a == 0 gives 0 (the seed is inf there: selected away); subnormal arguments are not supported.
+PCG_DEV double sqrt_fast(double a) {
+  double r;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(a));
+  double g = a * r, h = 0.5 * r;
+  const double e = fma(-h, g, 0.5);
+  g = fma(g, e, g);
+  h = fma(h, e, h);
+  g = fma(fma(-g, g, a), h, g);
+  return a == 0.0 ? a : g;
+}
+
+// log(x) for x > 0 (normal), branch-free: x = 2^e m, m in [1, 2); the top seven mantissa bits pick c_j with
+// r = m / c_j - 1 formed EXACTLY by one fma against a 12-bit reciprocal (|r| < 2^-7.9), and
+// log x = e ln2 + log c_j + (r - r^2/2 + r^3 (1/3 - r/4 + r^2/5 - r^3/6 + r^4/7))        (next term r^8/8 < 2e-20).
+// ~1 ulp (tools/gen_logtab.py --check: 3.6e-15 absolute at |log| = 30, 2e-15 relative), 12 FP64 + 1 conversion + one
+// 16-byte table load against ~45 instructions and three branches for the library's log.  x = 0 returns ~ -709 (its
+// exponent field), x < 0 the log of |x| (crystallization wants exp(k log|x|), ~0 at x = 0).  NaN or inf in, NaN out.
+struct LogTabConst { double ln2_hi, ln2_lo, c3, c4, c5, c6, c7; };
+static __constant__ LogTabConst kLT = {0.6931471803691238, 1.9082149292705877e-10, 1.0 / 3, -0.25, 0.2, -1.0 / 6, 1.0 / 7};
+static __device__ const double2 kLogTab[128] = {
+#define PCG_LT(a, b) {a, b}
+#include "logtab.inc"
+#undef PCG_LT
+};
+PCG_DEV double log_tab(double x) {
+  const int hi = __double2hiint(x);
+  const int e = ((hi >> 20) & 0x7ff) - 1023;
+  const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(x));
+  const double2 t = __ldg(&kLogTab[(hi >> 13) & 127]);
+  const double r = fma(m, t.x, -1.0);
+  const double ed = static_cast<double>(e);
+  double q = fma(kLT.c7, r, kLT.c6);
+  q = fma(q, r, kLT.c5);
+  q = fma(q, r, kLT.c4);
+  q = fma(q, r, kLT.c3);
+  const double p = fma(r * r, fma(r, q, -0.5), r);
+  return fma(ed, kLT.ln2_hi, t.y) + fma(ed, kLT.ln2_lo, fma(x, 0.0, p));   // x * 0: NaN (and inf) in, NaN out
+}
+
 // high word of a double, host or device (positive normal doubles order like their high words)
 PCG_HD int hi_word(double v) {
 #ifdef __CUDA_ARCH__

@@ -192,10 +192,11 @@ inline bool wsm_ok(const pcg_desc& d, const pcg_io& io, int64_t n_env, int64_t k
   return tiles >= 2 && tiles <= kWsmMaxTiles;
 }
 
-template <class M, class TB, int NOISE, int NSP, bool CONU, bool SPS, bool ADAPT>
+template <class M, class TB, int NOISE, int NSP, bool CONU, bool SPS, bool ADAPT, bool GEN>
 cudaError_t launch_wsm_n(const pcg_desc& d, const pcg_io& io, const Derived<M, TB>& dv, int64_t n_env, int t0,
                          int k_steps, cudaStream_t s, int64_t epc, int n_tiles) {
-  using Shared = WsmShared<M, NOISE, NSP, SPS>;
+  using L = WsmLayout<ADAPT, GEN>;
+  using Shared = WsmShared<M, NOISE, NSP, SPS, L::ring, GEN ? M::ND : 0>;
   static_assert(sizeof(Shared) <= 227 * 1024, "wsm_rollout_kernel: rings + tables exceed the 227 KB a CTA may opt in to");
   // > 48 KB of dynamic shared memory needs the opt-in, once per kernel instantiation AND device
   static std::atomic<uint64_t> opted{0};
@@ -203,42 +204,43 @@ cudaError_t launch_wsm_n(const pcg_desc& d, const pcg_io& io, const Derived<M, T
   if (cudaGetDevice(&dev) != cudaSuccess) dev = 0;
   const uint64_t bit = uint64_t{1} << (dev & 63);
   if (!(opted.load(std::memory_order_acquire) & bit)) {
-    const cudaError_t attr = cudaFuncSetAttribute(wsm_rollout_kernel<M, TB, NOISE, NSP, CONU, SPS, ADAPT>,
+    const cudaError_t attr = cudaFuncSetAttribute(wsm_rollout_kernel<M, TB, NOISE, NSP, CONU, SPS, ADAPT, GEN>,
                                                   cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                   static_cast<int>(sizeof(Shared)));
     if (attr != cudaSuccess) return attr;
     opted.fetch_or(bit, std::memory_order_release);
   }
   const unsigned grid = static_cast<unsigned>((n_env + epc - 1) / epc);
-  wsm_rollout_kernel<M, TB, NOISE, NSP, CONU, SPS, ADAPT>
-      <<<grid, 32 * WsmLayout<ADAPT>::warps, sizeof(Shared), s>>>(d, io, dv, n_env, t0, k_steps, epc, n_tiles);
+  wsm_rollout_kernel<M, TB, NOISE, NSP, CONU, SPS, ADAPT, GEN>
+      <<<grid, 32 * L::warps, sizeof(Shared), s>>>(d, io, dv, n_env, t0, k_steps, epc, n_tiles);
   return cudaGetLastError();
 }
 
-template <class M, class TB, int NSP, bool CONU, bool SPS, bool ADAPT>
+template <class M, class TB, int NSP, bool CONU, bool SPS, bool ADAPT, bool GEN>
 cudaError_t launch_wsm_s(const pcg_desc& d, const pcg_io& io, const Derived<M, TB>& dv, int64_t n_env, int t0,
                          int k_steps, cudaStream_t s, int64_t epc, int n_tiles) {
   switch (d.noise) {
     case PCG_NOISE_OFF:
-      return launch_wsm_n<M, TB, PCG_NOISE_OFF, NSP, CONU, SPS, ADAPT>(d, io, dv, n_env, t0, k_steps, s, epc, n_tiles);
+      return launch_wsm_n<M, TB, PCG_NOISE_OFF, NSP, CONU, SPS, ADAPT, GEN>(d, io, dv, n_env, t0, k_steps, s, epc, n_tiles);
     case PCG_NOISE_PHILOX:
-      return launch_wsm_n<M, TB, PCG_NOISE_PHILOX, NSP, CONU, SPS, ADAPT>(d, io, dv, n_env, t0, k_steps, s, epc, n_tiles);
+      return launch_wsm_n<M, TB, PCG_NOISE_PHILOX, NSP, CONU, SPS, ADAPT, GEN>(d, io, dv, n_env, t0, k_steps, s, epc, n_tiles);
     default:
-      if constexpr (ADAPT) return cudaErrorNotSupported;       // launch_e keeps fp32-evaluated noise on the generic kernel
-      else return launch_wsm_n<M, TB, PCG_NOISE_PHILOX_F32, NSP, CONU, SPS, ADAPT>(d, io, dv, n_env, t0, k_steps, s, epc, n_tiles);
+      // launch_e keeps fp32-evaluated noise on the generic kernel for the adaptive and the general variant
+      if constexpr (ADAPT || GEN) return cudaErrorNotSupported;
+      else return launch_wsm_n<M, TB, PCG_NOISE_PHILOX_F32, NSP, CONU, SPS, ADAPT, GEN>(d, io, dv, n_env, t0, k_steps, s, epc, n_tiles);
   }
 }
 
-template <class M, class TB, int NSP, bool CONU, bool ADAPT>
+template <class M, class TB, int NSP, bool CONU, bool ADAPT, bool GEN>
 cudaError_t launch_wsm_c(const pcg_desc& d, const pcg_io& io, const Derived<M, TB>& dv, int64_t n_env, int t0,
                          int k_steps, cudaStream_t s, int64_t epc, int n_tiles) {
   // the reference's setpoints are ONE schedule for every env (SP[k][t], pcgym.py:432-438): staged in shared memory
   const bool sps = io.sp_se == 0 && k_steps + 1 <= kWsmSpMax;
-  return sps ? launch_wsm_s<M, TB, NSP, CONU, true, ADAPT>(d, io, dv, n_env, t0, k_steps, s, epc, n_tiles)
-             : launch_wsm_s<M, TB, NSP, CONU, false, ADAPT>(d, io, dv, n_env, t0, k_steps, s, epc, n_tiles);
+  return sps ? launch_wsm_s<M, TB, NSP, CONU, true, ADAPT, GEN>(d, io, dv, n_env, t0, k_steps, s, epc, n_tiles)
+             : launch_wsm_s<M, TB, NSP, CONU, false, ADAPT, GEN>(d, io, dv, n_env, t0, k_steps, s, epc, n_tiles);
 }
 
-template <class M, class TB, bool ADAPT = false>
+template <class M, class TB, bool ADAPT = false, bool GEN = false>
 cudaError_t launch_wsm(const pcg_desc& d0, const pcg_io& io, int64_t n_env, int t0, int k_steps, cudaStream_t s,
                        int64_t epc, int n_tiles) {
   const pcg_desc d = fold_desc<M>(d0);
@@ -247,14 +249,43 @@ cudaError_t launch_wsm(const pcg_desc& d0, const pcg_io& io, int64_t n_env, int 
   for (int c = 0; c < d.n_con; ++c) con_u = con_u || d.con_mask_u[c] != 0;
   cudaError_t e;
   if (d.nsp == 1)
-    e = con_u ? launch_wsm_c<M, TB, 1, true, ADAPT>(d, io, dv, n_env, t0, k_steps, s, epc, n_tiles)
-              : launch_wsm_c<M, TB, 1, false, ADAPT>(d, io, dv, n_env, t0, k_steps, s, epc, n_tiles);
+    e = con_u ? launch_wsm_c<M, TB, 1, true, ADAPT, GEN>(d, io, dv, n_env, t0, k_steps, s, epc, n_tiles)
+              : launch_wsm_c<M, TB, 1, false, ADAPT, GEN>(d, io, dv, n_env, t0, k_steps, s, epc, n_tiles);
   else
-    e = con_u ? launch_wsm_c<M, TB, 2, true, ADAPT>(d, io, dv, n_env, t0, k_steps, s, epc, n_tiles)
-              : launch_wsm_c<M, TB, 2, false, ADAPT>(d, io, dv, n_env, t0, k_steps, s, epc, n_tiles);
+    e = con_u ? launch_wsm_c<M, TB, 2, true, ADAPT, GEN>(d, io, dv, n_env, t0, k_steps, s, epc, n_tiles)
+              : launch_wsm_c<M, TB, 2, false, ADAPT, GEN>(d, io, dv, n_env, t0, k_steps, s, epc, n_tiles);
   t_last_kernel = ADAPT ? "wsm_rollout_kernel (persistent CTA per SM, adaptive integrator warps + finisher pool)"
+                  : GEN ? "wsm_rollout_kernel (persistent CTA per SM, general: disturbance rows + substeps)"
                         : "wsm_rollout_kernel (persistent CTA per SM: integrator warps + finisher pool)";
   return e;
+}
+
+// The general variant of the per-SM kernel (GEN) takes what used to send a cstr batch to the generic kernel although
+// everything else fits the straight-line form: supplied model disturbances (per-env tables or the reference's shared
+// schedule), observed disturbance slots, n_sub > 1 fixed substeps.  Still excluded: per-env parameters, uncertain-
+// parameter tail, > 2 setpoints / constraints, constraints that read observation slots, a_delta, other rewards,
+// external / fp32 noise.
+template <class M>
+inline bool wsm_gen_ok(const pcg_desc& d, const pcg_io& io, int64_t n_env, int64_t k_steps, int64_t* epc, int* tiles) {
+  if (d.flags & PCG_F_ADAPTIVE) return false;
+  if (d.nd == 0 && d.n_sub == 1) return false;                 // the plain variant's job
+  if (io.theta != nullptr || d.n_tail > 0 || d.nd_obs > M::ND) return false;
+  if ((d.flags & PCG_F_A_DELTA) && (d.flags & PCG_F_NORMALISE_A)) return false;
+  if (d.reward != PCG_REWARD_SP || d.nsp < 1 || d.nsp > kFastNsp || d.n_con > kFastNcon) return false;
+  for (int c = 0; c < d.n_con; ++c)
+    if (d.con_mask_x[c] >> M::NX) return false;
+  if (d.noise != PCG_NOISE_OFF && d.noise != PCG_NOISE_PHILOX) return false;
+  if (!io.x_traj || !io.obs || !io.reward || !io.done || !io.violated || (d.n_con > 0 && !io.g)) return false;
+  if (d.nd > 0) {
+    bool any = false;
+    for (int i = 0; i < M::ND; ++i) any = any || d.d_src[i] >= 0;
+    if (any) {
+      if (!io.dist || io.d_se < 0 || io.d_se > 1) return false;
+      // per-env tables move as 16-byte pairs: even strides, aligned base
+      if (io.d_se == 1 && (!al16(io.dist) || (io.d_st % 2) != 0 || (io.d_sj % 2) != 0)) return false;
+    }
+  }
+  return wsm_ok<M>(d, io, n_env, k_steps, epc, tiles);
 }
 
 // Kernel-family request of the calling thread (pcg_set_kernel; PCG_KERNEL_AUTO = the library's own choice).  A request
@@ -320,6 +351,14 @@ cudaError_t launch_e(const pcg_desc& d, const pcg_io& io, int64_t n_env, int t0,
 
 template <class M, class TB, bool ADAPTIVE>
 cudaError_t launch_g(const pcg_desc& d, const pcg_io& io, int64_t n_env, int t0, int k_steps, cudaStream_t s) {
+  if constexpr (!ADAPTIVE && M::FAST && M::EPT == 2 && M::WS > 0 && std::is_same<TB, Tsit5>::value) {   // one tableau: 16 instantiations
+    const int req = kernel_request();
+    int64_t epc = 0;
+    int tiles = 0;
+    if ((req == PCG_KERNEL_AUTO || req == PCG_KERNEL_WSM) && ept_override() != 1 && vector_ok(io, n_env) &&
+        d.env_id0 % 2 == 0 && wsm_gen_ok<M>(d, io, n_env, k_steps, &epc, &tiles))
+      return launch_wsm<typename M::WsmModel, TB, false, true>(d, io, n_env, t0, k_steps, s, epc, tiles);
+  }
   return (needs_general<M>(d) || io.theta != nullptr) ? launch_e<M, TB, ADAPTIVE, true>(d, io, n_env, t0, k_steps, s)
                              : launch_e<M, TB, ADAPTIVE, false>(d, io, n_env, t0, k_steps, s);
 }

@@ -319,8 +319,9 @@ struct FourTank {
   static constexpr int EPT = 1, MIN_BLOCKS = 4, MIN_BLOCKS_EPT1 = 4, WS = 0;
   static constexpr bool FAST = true;
   PCG_DEV static void rhs(const P& p, const Aux&, const double* x, const double* u, double* dx) {
-    const double s1 = sqrt(p.g2 * x[0]), s2 = sqrt(p.g2 * x[1]);   // NaN for h < 0, as the reference
-    const double s3 = sqrt(p.g2 * x[2]), s4 = sqrt(p.g2 * x[3]);
+    // sqrt_fast: branch-free (the four roots interleave in one basic block), NaN for h < 0 as the reference's np.sqrt
+    const double s1 = sqrt_fast(p.g2 * x[0]), s2 = sqrt_fast(p.g2 * x[1]);
+    const double s3 = sqrt_fast(p.g2 * x[2]), s4 = sqrt_fast(p.g2 * x[3]);
     dx[0] = fma(p.o11, s1, fma(p.o13, s3, p.p11 * u[0]));          // :906
     dx[1] = fma(p.o22, s2, fma(p.o24, s4, p.p22 * u[1]));          // :907
     dx[2] = fma(p.o33, s3, p.p32 * u[1]);                          // :908
@@ -338,21 +339,28 @@ struct Crystallization {
   PCG_HD static P make(const double* th) {
     return P{th[0], th[1], th[2], th[3], th[4], th[5], th[6], th[7], th[8], 0.5 * th[10] * th[9]};
   }
-  struct Aux {};
-  PCG_DEV static void prep(const P&, const double*, Aux&) {}
+  // per-interval constants: the jacket temperature is held over the control interval, so the solubility polynomial and
+  // the two Arrhenius exponents' temperature terms are hoisted out of the right-hand side
+  struct Aux { double ceq, b_t, g_t; };
+  PCG_DEV static void prep(const P& p, const double* u, Aux& a) {
+    const double TK = u[0] + 273.15;
+    const double inv_TK = 1.0 / TK;
+    a.ceq = fma(TK, fma(-0.00292874, TK, 3.579165), -686.2686);                 // :1302
+    a.b_t = p.kb * inv_TK;
+    a.g_t = p.k1 * inv_TK;
+  }
   PCG_HD static constexpr int dpar(int i) { constexpr int t[] = {0, 4, -1}; return t[i]; }   // "UA" is not a parameter of this model
   static constexpr int EPT = 1, MIN_BLOCKS = 4, MIN_BLOCKS_EPT1 = 4, WS = 0;
   static constexpr bool FAST = true;
-  PCG_DEV static void rhs(const P& p, const Aux&, const double* x, const double* u, double* dx) {
+  // Branch-free arithmetic (fastmath.cuh: table log, exp_sat, Newton reciprocal, Goldschmidt sqrt; each within ~1 ulp):
+  // the library versions carry slow-path branches and ~330 instructions per evaluation, this form ~150.
+  PCG_DEV static void rhs(const P& p, const Aux& a, const double* x, const double*, double* dx) {
     const double mu0 = x[0], mu1 = x[1], mu2 = x[2], mu3 = x[3], conc = x[4];
-    const double TK = u[0] + 273.15;
-    const double Ceq = fma(TK, fma(-0.00292874, TK, 3.579165), -686.2686);      // :1302
-    const double S = fma(conc, 1e3, -Ceq);                                      // :1303
-    const double inv_TK = 1.0 / TK;
-    const double lnS = log(fabs(S));            // (S^2)^(k/2) = |S|^k = exp(k ln|S|)
-    const double lnM = log(fabs(mu3));
-    const double B0 = p.ka * exp(fma(p.kb, inv_TK, fma(p.kc, lnS, p.kd * lnM)));   // :1304
-    const double G = p.kg * exp(fma(p.k1, inv_TK, p.k2 * lnS));                    // :1305
+    const double S = fma(conc, 1e3, -a.ceq);                                    // :1303
+    const double lnS = log_tab(S);              // (S^2)^(k/2) = |S|^k = exp(k ln|S|); log_tab takes |x|
+    const double lnM = log_tab(mu3);
+    const double B0 = p.ka * exp_sat(fma(p.kc, lnS, fma(p.kd, lnM, a.b_t)));    // :1304
+    const double G = p.kg * exp_sat(fma(p.k2, lnS, a.g_t));                     // :1305
     const double d0 = B0;
     const double d1 = G * fma(p.a, mu0, p.b * mu1 * 1e-4) * 1e4;                   // :1308
     const double d2 = 2.0 * G * fma(p.a * mu1, 1e-4, p.b * mu2 * 1e-8) * 1e8;      // :1309
@@ -360,10 +368,10 @@ struct Crystallization {
     const double d3 = 3.0 * G * m23 * 1e12;                                        // :1310
     const double dc = -p.half_ro_alfa * G * m23;                                   // :1311
     const double mu1sq = mu1 * mu1;
-    const double CV = sqrt(mu2 * mu0 / mu1sq - 1.0);                               // :1313
+    const double CV = sqrt_fast(mu2 * mu0 * rcp_nr(mu1sq) - 1.0);                  // :1313
     const double num = fma(fma(d2, mu0, mu2 * d0), mu1sq, -(mu2 * mu0 * 2.0 * mu1 * d1));
-    const double dCV = (1.0 / fma(2.0, CV, 1e-10)) * num / fma(mu1sq, mu1sq, 1e-10);   // :1314
-    const double dLn = fma(d1, mu0, -(mu1 * d0)) / fma(mu0, mu0, 1e-10);           // :1315
+    const double dCV = rcp_nr(fma(2.0, CV, 1e-10)) * num * rcp_nr(fma(mu1sq, mu1sq, 1e-10));   // :1314
+    const double dLn = fma(d1, mu0, -(mu1 * d0)) * rcp_nr(fma(mu0, mu0, 1e-10));   // :1315
     dx[0] = d0; dx[1] = d1; dx[2] = d2; dx[3] = d3; dx[4] = dc; dx[5] = dCV; dx[6] = dLn;
   }
 };

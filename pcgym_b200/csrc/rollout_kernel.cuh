@@ -708,7 +708,7 @@ rollout_kernel(const __grid_constant__ pcg_desc d, const __grid_constant__ pcg_i
               double o[3];
 #pragma unroll
               for (int i = 0; i < 3; ++i) o[i] = fma(z[e][i % NX] * x[e][i % NX], d.noise_pct[i % NX], x[e][i % NX]);
-              xo = (j == 0) ? sqrt(o[2] * o[0] / (o[1] * o[1]) - 1.0) : o[1] / o[0];
+              xo = (j == 0) ? sqrt_fast(o[2] * o[0] * rcp_nr(o[1] * o[1]) - 1.0) : o[1] * rcp_nr(o[0]);
             } else {
 #pragma unroll
               for (int i = 0; i < NX; ++i) {
@@ -721,7 +721,7 @@ rollout_kernel(const __grid_constant__ pcg_desc d, const __grid_constant__ pcg_i
           }
 #pragma unroll
         for (int j = 0; j < NU; ++j) {
-          const double inv = 0.5 / d.a_scale[j];                               // 1 / (a_hi - a_lo)
+          const double inv = 0.5 * rcp_nr(d.a_scale[j]);                       // 1 / (a_hi - a_lo)
           const double un = (uk[e][j] - (d.a_off[j] - d.a_scale[j])) * inv;
           const double up = ((u_prev_valid ? u_prev[e][j] : uk[e][j]) - (d.a_off[j] - d.a_scale[j])) * inv;
           const double du = (d.ocp_mode & 3) == 0 ? un : un - up;

@@ -73,14 +73,22 @@ static_assert(kWsmRing >= kWsmMaxFin && (kWsmRing & (kWsmRing - 1)) == 0, "ring 
 // default scheme).  The controller keeps six stage derivatives and two candidate states live and an interval costs
 // ~2.5 fixed steps, so the finishers have 2.5x less to do per unit time: 20 warps x 96 registers, 16 integrator-class
 // warps + 4 finishers, no register hand-over (setmaxnreg moves registers only inside the CTA's own allocation).
-template <bool ADAPT>
+// GEN = the GENERAL variant (BASELINE config 5's cstr part and the paper scripts' disturbance runs): per-interval model
+// disturbances travel through the ring as extra rows beside the action rows (dist[t + 1]; per-env tables by 16-byte
+// cp.async, the reference's shared schedule by two 8-byte ones), observed disturbance slots are appended to the
+// observation, and the integrator warps loop over n_sub fixed substeps.  Two more rows per slot do not fit 16-slot rings
+// (8 tiles x 16 slots x 5 rows x 512 B = 320 KB), so GEN runs 8-slot rings with 24 warps (16 x 64 + 8 x 96 registers).
+template <bool ADAPT, bool GEN = false>
 struct WsmLayout {
-  static constexpr int warps = ADAPT ? 20 : kWsmWarps;
+  static constexpr int ring = GEN ? 8 : kWsmRing;
+  static constexpr int max_fin = ring;                         // see "Ring depth" above
+  static constexpr int warps = ADAPT ? 20 : (GEN ? 24 : kWsmWarps);
   static constexpr int launch_regs = (65536 / (32 * warps)) / 8 * 8;
-  static constexpr int int_regs = ADAPT ? launch_regs : (PCG_WSM_INT_REGS ? PCG_WSM_INT_REGS : launch_regs);
-  static constexpr int fin_regs = ADAPT ? launch_regs : (PCG_WSM_INT_REGS ? PCG_WSM_FIN_REGS : launch_regs);
+  static constexpr int int_regs = ADAPT ? launch_regs : (GEN ? 64 : (PCG_WSM_INT_REGS ? PCG_WSM_INT_REGS : launch_regs));
+  static constexpr int fin_regs = ADAPT ? launch_regs : (GEN ? 96 : (PCG_WSM_INT_REGS ? PCG_WSM_FIN_REGS : launch_regs));
   static_assert(16 * (launch_regs - int_regs) >= (warps - 16) * (fin_regs - launch_regs),
                 "setmaxnreg budgets do not fit the CTA's register allocation");
+  static_assert(!(ADAPT && GEN), "the general variant is fixed-step");
 };
 
 template <int N> PCG_DEV void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
@@ -88,6 +96,9 @@ template <int N> PCG_DEV void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sy
 
 PCG_DEV void cp_async16(void* smem, const void* gmem) {          // 16 bytes global -> shared, no register staging
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem)), "l"(gmem) : "memory");
+}
+PCG_DEV void cp_async8(void* smem, const void* gmem) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(smem)), "l"(gmem) : "memory");
 }
 // arrive on `b` once every cp.async this thread issued before has landed (counts as one of the expected arrivals)
 PCG_DEV void cp_async_arrive(uint64_t* b) {
@@ -98,9 +109,18 @@ constexpr int kWsmSpMax = 256;     // staged setpoint schedule: k_steps + 1 <= k
 
 // NOISE / SPS decide which tables the CTA stages: the inverse-normal-CDF coefficients (16 KB) only when the finishers
 // draw in fp64, the setpoint schedule only when it is shared by all envs (the reference's form: io.sp_se == 0)
-template <class M, int NOISE, int NSP, bool SPS>
+// ring of one 64-env tile: as WsPair, with NDR extra input rows per slot (GEN: the model's disturbance channels)
+template <class M, int RING, int NDR>
+struct WsmTile {
+  double2 a[RING][M::NU + NDR][32];
+  double2 x[RING][M::NX][32];
+  uint64_t full_a[RING];
+  uint64_t full_x[RING];
+};
+
+template <class M, int NOISE, int NSP, bool SPS, int RING = kWsmRing, int NDR = 0>
 struct WsmShared {
-  WsPair<M, kWsmRing> tile[kWsmMaxTiles];
+  WsmTile<M, RING, NDR> tile[kWsmMaxTiles];
   uchar2 done0[kWsmMaxTiles][32];   // sticky done flag each env entered the launch with
   int next_task;
   double exp_tab[exp_tab_doubles<M>()];               // 2^(j/256) for exp_tab_split, or the direct table of exp_wide_split (integrator warps)
@@ -111,14 +131,16 @@ struct WsmShared {
 // NSP = number of setpoints (1 or 2), CONU = some constraint reads an input, SPS = the setpoint schedule is shared by
 // all envs and short enough to be staged in shared memory: compile-time, so the finisher carries no dead reward /
 // setpoint / input-column work and no branch for it
-template <class M, class TB, int NOISE, int NSP, bool CONU, bool SPS, bool ADAPT = false>
-__global__ void __launch_bounds__(32 * WsmLayout<ADAPT>::warps, 1)
+template <class M, class TB, int NOISE, int NSP, bool CONU, bool SPS, bool ADAPT = false, bool GEN = false>
+__global__ void __launch_bounds__(32 * WsmLayout<ADAPT, GEN>::warps, 1)
 wsm_rollout_kernel(const __grid_constant__ pcg_desc d, const __grid_constant__ pcg_io io,
                    const __grid_constant__ Derived<M, TB> dv, const int64_t n, const int t0, const int k_steps,
                    const int64_t envs_per_cta, const int n_tiles) {
-  constexpr int NX = M::NX, NU = M::NU, ND = M::ND, NUK = NU + ND, EPT = 2, R = kWsmRing;
+  using L = WsmLayout<ADAPT, GEN>;
+  constexpr int NX = M::NX, NU = M::NU, ND = M::ND, NUK = NU + ND, EPT = 2, R = L::ring, NDR = GEN ? ND : 0;
+  using Tile = WsmTile<M, R, NDR>;
   extern __shared__ __align__(16) unsigned char wsm_raw[];
-  using Shared = WsmShared<M, NOISE, NSP, SPS>;
+  using Shared = WsmShared<M, NOISE, NSP, SPS, R, NDR>;
   Shared& sh = *reinterpret_cast<Shared*>(wsm_raw);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t cta_base = static_cast<int64_t>(blockIdx.x) * envs_per_cta;
@@ -153,28 +175,51 @@ wsm_rollout_kernel(const __grid_constant__ pcg_desc d, const __grid_constant__ p
   }
   __syncthreads();
 
-  auto to_uk = [&](const double (&a_raw)[NU][EPT], double (&uk)[EPT][NUK]) {   // pcgym.py:372-375, 386-414
+  // a_raw rows [0, NU) are the action rows, rows [NU, NU + NDR) the supplied disturbance values of the interval (GEN)
+  auto to_uk = [&](const double (&a_raw)[NU + NDR][EPT], double (&uk)[EPT][NUK]) {   // pcgym.py:372-375, 386-414
 #pragma unroll
     for (int e = 0; e < EPT; ++e) {
 #pragma unroll
       for (int j = 0; j < NU; ++j) uk[e][j] = fma(a_raw[j][e], d.a_scale[j], d.a_off[j]);
 #pragma unroll
-      for (int i = 0; i < ND; ++i) uk[e][NU + i] = d.d_default[i];
+      for (int i = 0; i < ND; ++i) {
+        double v = d.d_default[i];
+        if constexpr (GEN) v = d.d_src[i] >= 0 ? a_raw[NU + i][e] : v;
+        uk[e][NU + i] = v;
+      }
+    }
+  };
+  // GEN: stage the supplied disturbance rows of time index tt (= t + 1 of the interval, pcgym.py:386-412) for this lane's
+  // env pair into ring slot s of tile `sp`.  Per-env tables are contiguous along the env axis (16-byte copies; the
+  // launcher checks alignment), the reference's shared schedule is one value for every env (two 8-byte copies).
+  auto stage_dist = [&](Tile& sp, int s, int lane_, int64_t env0_, int tt) {
+    if constexpr (GEN) {
+#pragma unroll
+      for (int i = 0; i < ND; ++i) {
+        if (d.d_src[i] >= 0) {
+          const double* src = io.dist + static_cast<int64_t>(tt) * io.d_st + d.d_src[i] * io.d_sj + env0_ * io.d_se;
+          if (io.d_se != 0) {
+            cp_async16(&sp.a[s][NU + i][lane_], src);
+          } else {
+            cp_async8(&sp.a[s][NU + i][lane_].x, src);
+            cp_async8(&sp.a[s][NU + i][lane_].y, src);
+          }
+        }
+      }
     }
   };
 
   // first finisher warp / number of finishers (warps between the two roles, and past the last finisher, retire)
   const int fin0 = kWsmIntClass ? kWsmIntClass : n_int;
-  using L = WsmLayout<ADAPT>;
   static_assert(!ADAPT || (EPI == 1 && TB::EMBEDDED), "adaptive integrator warps carry one env per lane");
-  const int n_fin = (L::warps - fin0) < kWsmMaxFin ? (L::warps - fin0) : kWsmMaxFin;
+  const int n_fin = (L::warps - fin0) < L::max_fin ? (L::warps - fin0) : L::max_fin;
   if (warp < fin0) {
     if constexpr (kWsmIntClass != 0 && L::int_regs < L::launch_regs) setmaxnreg_dec<L::int_regs>();   // whole warpgroups: warps 0..15
     if (warp >= n_int) return;
     // ================================================================ integrator warp: tile p, env 2 lane + h (+ e)
     const int p = warp / IPT, h = (warp % IPT) * EPI;
     if (lane >= tile_lanes(p)) return;
-    WsPair<M, R>& sp = sh.tile[p];
+    Tile& sp = sh.tile[p];
     const int64_t env0 = cta_base + static_cast<int64_t>(p) * 64 + 2 * lane + h;
     double x[EPI][NX];
 #pragma unroll
@@ -202,7 +247,11 @@ wsm_rollout_kernel(const __grid_constant__ pcg_desc d, const __grid_constant__ p
         for (int j = 0; j < NU; ++j)
           uk[e][j] = fma(reinterpret_cast<const double*>(&sp.a[s][j][lane])[h + e], d.a_scale[j], d.a_off[j]);
 #pragma unroll
-        for (int i = 0; i < ND; ++i) uk[e][NU + i] = d.d_default[i];
+        for (int i = 0; i < ND; ++i) {
+          double v = d.d_default[i];
+          if constexpr (GEN) v = d.d_src[i] >= 0 ? reinterpret_cast<const double*>(&sp.a[s][NU + (GEN ? i : 0)][lane])[h + e] : v;
+          uk[e][NU + i] = v;
+        }
       }
       typename M::Aux aux[EPI];
 #pragma unroll
@@ -212,6 +261,9 @@ wsm_rollout_kernel(const __grid_constant__ pcg_desc d, const __grid_constant__ p
       }
       if constexpr (ADAPT) {                                                   // integrator.py:65-88 (Tsit5 + PID 1e-8)
         advance_adaptive_aux<M, TB>(dv, dv.p, aux[0], x[0], uk[0], d.dt, d.rtol, d.atol, d.max_steps, h_carry, n_rhs, st_adapt);
+      } else if constexpr (GEN) {
+#pragma unroll 1
+        for (int sub = 0; sub < d.n_sub; ++sub) rk_step_fixed<M, TB, EPI>(dv, aux, x, uk);
       } else {
         rk_step_fixed<M, TB, EPI>(dv, aux, x, uk);                             // integrator.py:90-107
       }
@@ -232,7 +284,7 @@ wsm_rollout_kernel(const __grid_constant__ pcg_desc d, const __grid_constant__ p
         io.x[i * n + env0 + e] = x[e][i];
       }
       if (io.status && status) io.status[env0 + e] |= static_cast<uint8_t>(status);
-      if (io.n_rhs) io.n_rhs[env0 + e] += ADAPT ? n_rhs : k_steps * TB::S;
+      if (io.n_rhs) io.n_rhs[env0 + e] += ADAPT ? n_rhs : k_steps * TB::S * (GEN ? d.n_sub : 1);
     }
     if (ADAPT && io.h_carry) io.h_carry[env0] = h_carry;
     return;
@@ -244,7 +296,7 @@ wsm_rollout_kernel(const __grid_constant__ pcg_desc d, const __grid_constant__ p
   if (fin >= n_fin) return;
   const int flags = d.flags;
   const int nsp = d.nsp, n_con = d.n_con;
-  const int nsp_obs = (flags & PCG_F_SP_HIDDEN) ? 0 : nsp, n_obs = NX + nsp_obs;
+  const int nsp_obs = (flags & PCG_F_SP_HIDDEN) ? 0 : nsp, nd_obs = GEN ? d.nd_obs : 0, n_obs = NX + nsp_obs + nd_obs;
   const double pen = d.penalty;
   const PhiloxKeys& key = dv.rk;
   const int t_last = d.N - 1;
@@ -281,12 +333,23 @@ wsm_rollout_kernel(const __grid_constant__ pcg_desc d, const __grid_constant__ p
 #pragma unroll 1
   for (int p = fin; p < n_tiles; p += n_fin) {
     if (lane >= tile_lanes(p)) continue;
-    WsPair<M, R>& sp = sh.tile[p];
+    Tile& sp = sh.tile[p];
     const int64_t env0 = cta_base + static_cast<int64_t>(p) * 64 + 2 * lane;
     const double* pa = io.a + env0;
-    double a0[NU][EPT];
+    double a0[NU + NDR][EPT];
 #pragma unroll
     for (int j = 0; j < NU; ++j) ld_row<EPT>(pa + j * n, a0[j]);
+    if constexpr (GEN) {                                                       // dist[t0 + 1] for the pre-check's input vector
+#pragma unroll
+      for (int i = 0; i < ND; ++i) {
+        a0[NU + i][0] = a0[NU + i][1] = 0.0;
+        if (d.d_src[i] >= 0) {
+          const double* src = io.dist + static_cast<int64_t>(t0 + 1) * io.d_st + d.d_src[i] * io.d_sj + env0 * io.d_se;
+          a0[NU + i][0] = src[0];
+          a0[NU + i][1] = src[io.d_se];
+        }
+      }
+    }
     sh.done0[p][lane] = io.done_state ? *reinterpret_cast<const uchar2*>(io.done_state + env0) : make_uchar2(0, 0);
     if (t0 == 0 && n_con > 0) {                                                // pcgym.py:416-420
       double x0[EPT][NX], uk0[EPT][NUK];
@@ -306,6 +369,7 @@ wsm_rollout_kernel(const __grid_constant__ pcg_desc d, const __grid_constant__ p
       if (s < k_steps) {
 #pragma unroll
         for (int j = 0; j < NU; ++j) cp_async16(&sp.a[s][j][lane], pa + (static_cast<int64_t>(s) * NU + j) * n);
+        stage_dist(sp, s, lane, env0, t0 + s + 1);
         cp_async_arrive(&sp.full_a[s]);
       }
     }
@@ -333,7 +397,7 @@ wsm_rollout_kernel(const __grid_constant__ pcg_desc d, const __grid_constant__ p
 #endif
     const int k = static_cast<int>(__umulhi(static_cast<uint32_t>(q), tiles_rcp)), p = q - k * n_tiles;   // q / n_tiles
     if (lane >= tile_lanes(p)) continue;
-    WsPair<M, R>& sp = sh.tile[p];
+    Tile& sp = sh.tile[p];
     const int s = k & (R - 1);
     const int t = t0 + k, t_new = t + 1;                                       // pcgym.py:441
     const uint32_t env0 = static_cast<uint32_t>(cta_base) + static_cast<uint32_t>(p) * 64u + 2u * lane;
@@ -405,10 +469,10 @@ wsm_rollout_kernel(const __grid_constant__ pcg_desc d, const __grid_constant__ p
       xe[0][i] = v.x;
       xe[1][i] = v.y;
     }
-    if constexpr (CONU) {                                   // the input vector is only needed by such constraints
-      double a_raw[NU][EPT];
+    if constexpr (CONU || GEN) {                            // the input vector: constraints that read it, observed disturbances
+      double a_raw[NU + NDR][EPT];
 #pragma unroll
-      for (int j = 0; j < NU; ++j) {
+      for (int j = 0; j < NU + NDR; ++j) {
         const double2 v = sp.a[s][j][lane];
         a_raw[j][0] = v.x;
         a_raw[j][1] = v.y;
@@ -453,6 +517,20 @@ wsm_rollout_kernel(const __grid_constant__ pcg_desc d, const __grid_constant__ p
       for (int e = 0; e < EPT; ++e) w[e] = fma(spc[j][e], d.o_scale[NX + j], d.o_off[NX + j]);
       if (j < nsp_obs) st_row<EPT>(io.obs + (io_ + (NX + j) * n32), w);
     }
+    if constexpr (GEN) {                                    // observed disturbance slots (pcgym.py:386-412): value held over the interval
+#pragma unroll
+      for (int j = 0; j < ND; ++j) {
+        double w[EPT];
+#pragma unroll
+        for (int e = 0; e < EPT; ++e) {
+          double v = 0.0;
+#pragma unroll
+          for (int i = 0; i < ND; ++i) v = (d.d_obs[j] == i) ? uk[e][NU + i] : v;
+          w[e] = fma(v, d.o_scale[NX + nsp_obs + j], d.o_off[NX + nsp_obs + j]);
+        }
+        if (j < nd_obs) st_row<EPT>(io.obs + (io_ + (NX + nsp_obs + j) * n32), w);
+      }
+    }
     st_row<EPT>(io.reward + row, r);
     st_flags<EPT>(io.done + row, done);
     st_flags<EPT>(io.violated + row, violated);
@@ -461,6 +539,7 @@ wsm_rollout_kernel(const __grid_constant__ pcg_desc d, const __grid_constant__ p
 #pragma unroll
       for (int j = 0; j < NU; ++j)
         cp_async16(&sp.a[s][j][lane], io.a + ((static_cast<uint32_t>(k + R) * NU + j) * n32 + env0));
+      stage_dist(sp, s, lane, static_cast<int64_t>(env0), t + R + 1);
       cp_async_arrive(&sp.full_a[s]);
     }
     if (k == k_steps - 1 && io.done_state) {                                   // the sticky flag after this launch

@@ -525,6 +525,49 @@ def test_per_sm_kernel_every_tile_count_long_horizon(tiles):
     assert (a["violated"] == b["violated"]).double().mean() > 0.9999
 
 
+@pytest.mark.parametrize("per_env,n_sub,n", [(False, 1, 20000), (True, 1, 20000), (True, 2, 21846), (False, 3, 40000),
+                                             ("none", 2, 65536)])
+def test_general_per_sm_kernel_matches_the_generic_kernel(per_env, n_sub, n):
+    """The GENERAL variant of the per-SM kernel (disturbance rows through the ring, observed disturbance slots,
+    n_sub fixed substeps: what BASELINE config 5's cstr part needs) against the generic kernel on the same inputs:
+    the reference's shared disturbance schedule (docs/guides/disturbances.md) and per-env tables, one to three substeps,
+    constraints + penalty + noise on.  Same arithmetic up to the exponential's form in the integrator warps: states to
+    2e-12, everything derived from them to rounding, identical flags away from rounding-level constraint values."""
+    params = cases.cstr_dist_cons()
+    N = params["N"]
+    rng = np.random.default_rng(17)
+    if per_env == "none":
+        params.pop("disturbances"); params.pop("disturbance_bounds")
+    elif per_env:
+        params["disturbances"] = {"Ti": np.repeat(rng.uniform(340, 352, (n, (N + 3) // 4)), 4, axis=1)[:, :N],
+                                  "Caf": rng.uniform(0.9, 1.1, (n, N))}
+    else:
+        params["disturbances"] = {"Ti": np.repeat(rng.uniform(340, 352, N // 4), 4), "Caf": rng.uniform(0.9, 1.1, N)}
+    params.update(noise=True, noise_percentage=0.001, seed=9,
+                  integrator={"scheme": "tsit5", "adaptive": False, "n_sub": n_sub})
+    acts = torch.as_tensor(rng.uniform(-1, 1, (N - 1, 1, n))).cuda()
+    outs = []
+    for req, want in (("auto", "wsm_rollout_kernel (persistent CTA per SM, general"), ("generic", "rollout_kernel (generic")):
+        with forced_kernel(req) as fk:
+            env = _env(params, n_envs=n)
+            env.reset()
+            out = env.rollout(acts)
+            torch.cuda.synchronize()
+            assert fk.last().startswith(want), (req, fk.last())
+            assert int(env.status.max()) == 0
+            outs.append(({k: out[k].cpu().numpy().astype(np.float64) for k in ("x", "obs", "reward", "done", "violated")},
+                         env.info["cons_info"].cpu().numpy(), env.rhs_evaluations.cpu().numpy()))
+    (a, ga, ra), (b, gb, rb) = outs
+    assert a["obs"].shape[1] == (3 if per_env == "none" else 5)              # [Ca, T, SP, Ti, Caf]
+    assert rel(a["x"], b["x"]) < 2e-12
+    np.testing.assert_allclose(a["obs"], b["obs"], rtol=0, atol=1e-10)
+    np.testing.assert_allclose(ga, gb, rtol=0, atol=1e-9)
+    ok = a["violated"] == b["violated"]
+    assert ok.mean() > 0.9999 and a["violated"].any()
+    np.testing.assert_allclose(a["reward"][ok], b["reward"][ok], rtol=1e-9, atol=1e-12)
+    assert np.array_equal(a["done"], b["done"]) and np.array_equal(ra, rb)
+
+
 @pytest.mark.parametrize("n", [65536, 20000])
 def test_default_adaptive_scheme_in_the_per_sm_kernel(n):
     """make_env's DEFAULT integrator (adaptive Tsit5, rtol = atol = 1e-8, the reference's jax path integrator.py:65-88)
