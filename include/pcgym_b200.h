@@ -140,7 +140,9 @@ enum pcg_kernel {
   PCG_KERNEL_WS = 2,            /* ws_rollout_kernel: integrator / finisher warp pairs                           */
   PCG_KERNEL_WSM = 3,           /* wsm_rollout_kernel: persistent CTA per SM, finisher pool                      */
   PCG_KERNEL_FAST_EPT1 = 4,     /* fast_rollout_kernel with one environment per thread (64-bit row accesses)    */
-  PCG_KERNEL_GENERIC_EPT1 = 5   /* rollout_kernel with one environment per thread                               */
+  PCG_KERNEL_GENERIC_EPT1 = 5,  /* rollout_kernel with one environment per thread                               */
+  PCG_KERNEL_LANES = 6          /* lanes_rollout_kernel: one lane per model stage, lane-asynchronous intervals
+                                   (adaptive pairs on multistage_extraction and its ten-stage extension)        */
 };
 
 /* per-env status bits written to io.status */

@@ -112,7 +112,7 @@ SYMBOLS = {
     "pcg_set_kernel": (C.c_int, [C.c_int]),
 }
 
-KERNELS = {"auto": -1, "generic": 0, "fast": 1, "ws": 2, "wsm": 3, "fast_ept1": 4, "generic_ept1": 5}
+KERNELS = {"auto": -1, "generic": 0, "fast": 1, "ws": 2, "wsm": 3, "fast_ept1": 4, "generic_ept1": 5, "lanes": 6}
 
 _lib = None
 

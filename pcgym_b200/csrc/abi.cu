@@ -269,7 +269,7 @@ const char* pcg_last_cuda_error(void) { return t_cuda_err; }
 const char* pcg_last_kernel(void) { return pcg::t_last_kernel; }
 
 int pcg_set_kernel(int kernel) {
-  if (kernel < PCG_KERNEL_AUTO || kernel > PCG_KERNEL_GENERIC_EPT1) return PCG_E_RANGE;
+  if (kernel < PCG_KERNEL_AUTO || kernel > PCG_KERNEL_LANES) return PCG_E_RANGE;
   const int prev = pcg::t_kernel_request;
   pcg::t_kernel_request = kernel;
   return prev;

@@ -6,6 +6,7 @@
 #include <atomic>
 #include <cstdlib>
 
+#include "rollout_lanes.cuh"
 #include "rollout_wsm.cuh"
 
 namespace pcg {
@@ -307,6 +308,38 @@ inline int kernel_request() {
   return env;
 }
 
+// lane-split, lane-asynchronous adaptive kernel (rollout_lanes.cuh): staged models (M::LANES), embedded explicit pair,
+// lean observation vector, SP or no reward, no a_delta, Philox / external / no noise
+template <class M>
+inline bool lanes_ok(const pcg_desc& d, const pcg_io& io) {
+  if (!(d.flags & PCG_F_ADAPTIVE) || needs_general<M>(d) || io.theta != nullptr) return false;
+  if ((d.flags & PCG_F_A_DELTA) && (d.flags & PCG_F_NORMALISE_A)) return false;
+  if (d.reward != PCG_REWARD_SP && d.reward != PCG_REWARD_NONE) return false;
+  if (d.nsp > kFastNsp) return false;
+  if (d.noise == PCG_NOISE_PHILOX_F32 || (d.noise == PCG_NOISE_EXTERNAL && !io.z)) return false;
+  return M::lanes_ready(M::make(d.theta));
+}
+
+template <class M, class TB>
+cudaError_t launch_lanes(const pcg_desc& d, const pcg_io& io, int64_t n_env, int t0, int k_steps, cudaStream_t s) {
+  constexpr int epb = (32 / M::LANES) * (kLanesBlock / 32);                    // envs per CTA
+  const unsigned grid = static_cast<unsigned>((n_env + epb - 1) / epb);
+  const Derived<M, TB> dv = make_derived<M, TB>(d);
+  switch (d.noise) {
+    case PCG_NOISE_OFF:
+      lanes_rollout_kernel<M, TB, PCG_NOISE_OFF><<<grid, kLanesBlock, 0, s>>>(d, io, dv, n_env, t0, k_steps);
+      break;
+    case PCG_NOISE_PHILOX:
+      lanes_rollout_kernel<M, TB, PCG_NOISE_PHILOX><<<grid, kLanesBlock, 0, s>>>(d, io, dv, n_env, t0, k_steps);
+      break;
+    default:
+      lanes_rollout_kernel<M, TB, PCG_NOISE_EXTERNAL><<<grid, kLanesBlock, 0, s>>>(d, io, dv, n_env, t0, k_steps);
+      break;
+  }
+  t_last_kernel = "lanes_rollout_kernel (one lane per stage, lane-asynchronous control intervals)";
+  return cudaGetLastError();
+}
+
 template <class M, class TB, bool ADAPTIVE, bool GENERAL>
 cudaError_t launch_e(const pcg_desc& d, const pcg_io& io, int64_t n_env, int t0, int k_steps, cudaStream_t s) {
   const int req = kernel_request();
@@ -342,6 +375,10 @@ cudaError_t launch_e(const pcg_desc& d, const pcg_io& io, int64_t n_env, int t0,
           wsm_ok<M>(d, io, n_env, k_steps, &epc, &tiles) && (req == PCG_KERNEL_WSM || req == PCG_KERNEL_AUTO))
         return launch_wsm<typename M::WsmModel, TB, true>(d, io, n_env, t0, k_steps, s, epc, tiles);
     }
+  }
+  if constexpr (ADAPTIVE && !GENERAL && has_lanes<M>::value && TB::EMBEDDED && !is_rosenbrock<TB>::value) {
+    if (!generic && (req == PCG_KERNEL_AUTO || req == PCG_KERNEL_LANES) && lanes_ok<M>(d, io))
+      return launch_lanes<M, TB>(d, io, n_env, t0, k_steps, s);
   }
   if constexpr (!ADAPTIVE && M::EPT == 2) {
     if (two) return launch_one<M, TB, ADAPTIVE, GENERAL, 2>(d, io, n_env, t0, k_steps, s);

@@ -235,6 +235,29 @@ struct ExtractionT {
       dx[2 * i + 1] = p.inv_vg * fma(G, yin - Y, Q);
     }
   }
+  // Lane-split form (rollout_lanes.cuh): lane s of an env's group owns stage s, xl = (X_s, Y_s).  The liquid comes from
+  // the stage on the left, the gas from the stage on the right: one 64-bit shuffle each, executed by the whole warp.  The
+  // two ends of the column read the FEEDS (X0, Y6) from a spare lane of the warp that holds them as its "state" with
+  // all-zero coefficients (its derivative is exactly 0, so it stays put through every stage): no per-evaluation select.
+  // LaneC = the interval's coefficients (inputs folded in), optionally pre-multiplied by the step so that the evaluation
+  // returns h f directly.  Quadratic equilibrium only (the reference's default eq_exponent = 2: lanes_ready()).
+  static constexpr int LANES = NS;
+  PCG_HD static bool lanes_ready(const P& p) { return p.square; }
+  struct LaneC { double cl, cg, ql, qg; };
+  PCG_DEV static void lane_prep(const P& p, const double* u, bool live, LaneC& c) {
+    c.cl = live ? p.inv_vl * u[0] : 0.0;                         // L / Vl
+    c.cg = live ? p.inv_vg * u[1] : 0.0;                         // G / Vg
+    c.ql = live ? p.inv_vl * p.kla_vl : 0.0;                     // Kla
+    c.qg = live ? p.inv_vg * p.kla_vl : 0.0;                     // Kla Vl / Vg
+  }
+  PCG_DEV static void lane_feed(const double* u, double (&xl)[2]) { xl[0] = u[2]; xl[1] = u[3]; }   // (X0, Y6)
+  PCG_DEV static void rhs_lane(const P& p, const LaneC& c, const double (&xl)[2], int src_l, int src_r, double (&dxl)[2]) {
+    const double X = xl[0], Y = xl[1];
+    const double xin = __shfl_sync(0xffffffffu, X, src_l), yin = __shfl_sync(0xffffffffu, Y, src_r);
+    const double q = fma(-(Y * Y), p.inv_m, X);                  // X - Y^2 / m   (:387-397)
+    dxl[0] = fma(-c.ql, q, c.cl * (xin - X));                    // :399-410
+    dxl[1] = fma(c.qg, q, c.cg * (yin - Y));
+  }
   // Rosenbrock interface (scheme "rodas4"): with the states interleaved X1 Y1 X2 Y2 ... the Jacobian of the column is
   // pentadiagonal (X_i sees X_{i-1} two columns to the left and Y_i one to the right; Y_i sees X_i one to the left and
   // Y_{i+1} two to the right).  W = s I - J is a column-diagonally-dominant Z-matrix (the stage balances conserve mass),

@@ -568,6 +568,51 @@ def test_general_per_sm_kernel_matches_the_generic_kernel(per_env, n_sub, n):
     assert np.array_equal(a["done"], b["done"]) and np.array_equal(ra, rb)
 
 
+@pytest.mark.parametrize("model,n,scheme", [("multistage_extraction", 4099, "tsit5"), ("multistage_extraction", 32768, "dopri5"),
+                                            ("multistage_extraction_10stage", 1000, "tsit5")])
+def test_lane_split_kernel_matches_the_generic_adaptive_kernel(model, n, scheme):
+    """The lane-split, lane-asynchronous kernel (one lane per stage of the column, csrc/rollout_lanes.cuh) is what the
+    adaptive pairs run on for multistage_extraction: against the generic kernel (same controller; only the order of the
+    additions in the error norm differs, so the two agree to the controller's tolerance, not bitwise), with two
+    constraints that part of the population violates, penalty, measurement noise, batch sizes that leave a warp and a
+    group partial.  A rollout cut in three reproduces the single launch bit for bit (carried step size, sticky done)."""
+    K = 12
+    params, x0, acts, key, sp = batch_setup(model, n, K)
+    c_lo, c_hi = 0.9 * BATCH[model]["x0"][0], 1.02 * BATCH[model]["x0"][0]
+    params.update(constraints=lambda x, u: np.array([c_lo - x[0], x[0] - c_hi]), done_on_cons_vio=False, r_penalty=True,
+                  constraint_units="physical", noise=True, noise_percentage=0.002, seed=4,
+                  integrator={"scheme": scheme, "adaptive": True, "rtol": 1e-8, "atol": 1e-10})
+    a = torch.as_tensor(acts).cuda()
+    outs = []
+    for req, want in (("auto", "lanes_rollout_kernel"), ("generic", "rollout_kernel (generic")):
+        with forced_kernel(req) as fk:
+            env = _env(params)
+            env.reset()
+            out = env.rollout(a)
+            torch.cuda.synchronize()
+            assert fk.last().startswith(want), (req, fk.last())
+            assert int(env.status.max()) == 0
+            outs.append(({k: out[k].cpu().numpy().astype(np.float64) for k in ("x", "obs", "reward", "done", "violated")},
+                         env.info["cons_info"].cpu().numpy(), env.rhs_evaluations.cpu().numpy().astype(np.float64)))
+    (u, gu, ru), (v, gv, rv) = outs
+    assert rel(u["x"], v["x"]) < 2e-7, rel(u["x"], v["x"])
+    np.testing.assert_allclose(u["obs"], v["obs"], rtol=0, atol=1e-6)
+    np.testing.assert_allclose(gu, gv, rtol=0, atol=1e-7)
+    ok = u["violated"] == v["violated"]
+    assert ok.mean() > 0.999 and u["violated"].any() and not u["violated"].all()
+    np.testing.assert_allclose(u["reward"][ok], v["reward"][ok], rtol=1e-5, atol=1e-8)
+    assert np.array_equal(u["done"], v["done"])
+    assert abs(ru.mean() / rv.mean() - 1) < 0.02                     # the same work, up to a few step decisions
+    # against the converged solution (north-star rtol 1e-6)
+    xs, _ = oracle_batch(model, params, x0[:96], acts[:, :, :96], key, sp, 2048)
+    assert rel(u["x"][:, :, :96], xs) < 1e-6
+    # split rollout == single rollout, bit for bit
+    env = _env(params)
+    env.reset()
+    parts = [env.rollout(a[:1])["x"].clone(), env.rollout(a[1:5])["x"].clone(), env.rollout(a[5:])["x"].clone()]
+    assert same(torch.cat(parts), torch.as_tensor(u["x"]).cuda())
+
+
 @pytest.mark.parametrize("n", [65536, 20000])
 def test_default_adaptive_scheme_in_the_per_sm_kernel(n):
     """make_env's DEFAULT integrator (adaptive Tsit5, rtol = atol = 1e-8, the reference's jax path integrator.py:65-88)

@@ -102,5 +102,5 @@ def test_kernel_request_knob():
     L = nat.lib()
     assert L.pcg_set_kernel(nat.KERNELS["wsm"]) == nat.KERNELS["auto"]          # returns the previous request
     assert L.pcg_set_kernel(nat.KERNELS["auto"]) == nat.KERNELS["wsm"]
-    assert L.pcg_set_kernel(6) == -6 and L.pcg_set_kernel(-2) == -6
+    assert L.pcg_set_kernel(7) == -6 and L.pcg_set_kernel(-2) == -6
     assert L.pcg_set_kernel(nat.KERNELS["auto"]) == nat.KERNELS["auto"]
