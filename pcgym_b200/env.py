@@ -26,6 +26,8 @@ from __future__ import annotations
 import copy
 import ctypes
 
+import warnings
+
 import numpy as np
 import torch
 
@@ -124,6 +126,8 @@ class make_env:
         if integ["scheme"] == "rodas4":               # Rosenbrock 4(3): always step-size controlled
             integ["adaptive"] = True
         self.integrator = integ
+        self._fixed_checked = False
+        self.fixed_step_probe_error = None       # set by the first reset() of a fixed-step env (fixed_step_error)
 
         # pcgym.py:127-158
         if P.get("custom_model") is not None:
@@ -601,9 +605,72 @@ class make_env:
         self._desc.seed = key
         self._desc_step.seed = key
 
+    # ------------------------------------------------------------------ fixed-step accuracy probe
+    def fixed_step_error(self, n_probe: int = 512, intervals: int = 16, seed: int = 0) -> float:
+        """Worst relative state difference between THIS env's fixed-step integrator and a tight adaptive run (Tsit5,
+        rtol 1e-10) over a short probe rollout: `n_probe` envs from this env's own x0, uniform random actions over the
+        whole action range, the first `intervals` control intervals, disturbances / parameters as configured.  A fixed
+        step has no error estimate of its own (the headline scheme, Tsit5 x 1, holds the north-star 1e-6 at the
+        documented CSTR interval dt = 0.25 with a 3x margin, but not at every dt), so reset() runs this once for
+        fixed-step schemes and warns above 1e-6 (`integrator={"check": False}` turns it off).  Returns the error."""
+        if self.integrator.get("adaptive", True) or self.integrator.get("scheme") == "rodas4":
+            return 0.0
+        n = int(min(n_probe, self.n_envs))
+        K = int(max(1, min(intervals, self.N - 1)))
+
+        def rows(v):                                      # per-env tables keep their first n rows
+            a = v.detach().cpu().numpy() if isinstance(v, torch.Tensor) else np.asarray(v)
+            return a[:n] if (a.ndim == 2 and a.shape[0] == self.n_envs and self.n_envs > 1) else a
+        base = {k: v for k, v in self.env_params.items() if k not in ("custom_reward", "integrator")}
+        base.update(n_envs=n, noise=False, device=str(self.device))
+        if "x0" in base:
+            base["x0"] = rows(base["x0"])
+        if base.get("disturbances"):
+            base["disturbances"] = {k: rows(v) for k, v in base["disturbances"].items()}
+        if base.get("model_params"):
+            base["model_params"] = {k: (rows(v) if np.ndim(v) else v) for k, v in base["model_params"].items()}
+        g = torch.Generator(device="cpu").manual_seed(1234 + seed)
+        nu = self._a_lo.shape[0]
+        if self.normalise_a:
+            a = torch.rand(K, nu, n, generator=g, dtype=torch.float64) * 2 - 1
+        else:
+            lo, hi = torch.as_tensor(self._a_lo)[None, :, None], torch.as_tensor(self._a_hi)[None, :, None]
+            a = lo + (hi - lo) * torch.rand(K, nu, n, generator=g, dtype=torch.float64)
+        a = a.to(self.device)
+        xs = []
+        for integ in (dict(self.integrator, check=False),
+                      {"scheme": "tsit5", "adaptive": True, "rtol": 1e-10, "atol": 1e-12, "max_steps": 100000}):
+            e = make_env(dict(base, integrator=integ))
+            e.reset()
+            xs.append(e.rollout(a)["x"].clone())
+        ref = xs[1].abs().clamp_min(1e-300)
+        err = ((xs[0] - xs[1]).abs() / ref)
+        err = torch.where(torch.isfinite(err), err, torch.full_like(err, float("inf")))
+        return float(err.max())
+
+    def _check_fixed_step_once(self):
+        if self._fixed_checked or self.integrator.get("adaptive", True) or not self.integrator.get("check", True):
+            return
+        self._fixed_checked = True
+        try:
+            err = self.fixed_step_error()
+        except Exception as exc:  # noqa: BLE001  (advisory: a probe that cannot be built must not break reset())
+            warnings.warn(f"pcgym_b200: fixed-step accuracy probe skipped ({type(exc).__name__}: {exc})", RuntimeWarning)
+            return
+        self.fixed_step_probe_error = err
+        if not err <= 1e-6:
+            it = self.integrator
+            warnings.warn(
+                f"pcgym_b200: integrator {it.get('scheme')} with {it.get('n_sub', 1)} fixed step(s) per control interval "
+                f"(dt = {self.dt:g}) is {err:.1e} away from the converged solution on a probe rollout of this env -- the "
+                "reference's integrator (and the 1e-6 parity bar) need more substeps, or the default adaptive scheme "
+                "(integrator={'adaptive': True}); fixed steps carry no error estimate, so status stays 0",
+                RuntimeWarning, stacklevel=3)
+
     def reset(self, seed: int = 0, **kwargs):
         self._ensure_device()
         self._join_pipe()
+        self._check_fixed_step_once()
         self.t = 0
         self._begin_episode(kwargs.get("episode"))
         nx, n = self.Nx_oracle, self.n_envs

@@ -613,6 +613,35 @@ def test_lane_split_kernel_matches_the_generic_adaptive_kernel(model, n, scheme)
     assert same(torch.cat(parts), torch.as_tensor(u["x"]).cuda())
 
 
+def test_fixed_step_probe_warns_when_the_interval_is_too_long():
+    """A fixed step has no error estimate: the first reset() of a fixed-step env runs a short probe rollout against a
+    tight adaptive run and warns when the scheme is more than 1e-6 away (round-1 verdict: the headline's single Tsit5
+    step holds the bar at dt = 0.25 but nothing told a user who picked it at the reference's own dt = 0.433,
+    pc-gym_paper/.../cstr_visualisation.py:11-12).  Quiet at 0.25, loud at 0.433, off with integrator={"check": False}."""
+    import warnings
+    import bench
+    params, _ = bench.cstr_headline(n_envs=4096, device="cuda", seed=0)
+    with warnings.catch_warnings():
+        warnings.simplefilter("error")
+        env = _env(params)
+        env.reset()
+    assert 0 < env.fixed_step_probe_error < 1e-6
+    N = params["N"]
+    slow = dict(params, tsim=N * 0.433)
+    with pytest.warns(RuntimeWarning, match="away from the converged solution"):
+        env = _env(slow)
+        env.reset()
+    assert env.fixed_step_probe_error > 1e-6
+    with warnings.catch_warnings():
+        warnings.simplefilter("error")
+        env = _env(dict(slow, integrator=dict(slow["integrator"], check=False)))
+        env.reset()
+        assert env.fixed_step_probe_error is None
+        env = _env(dict(slow, integrator=dict(slow["integrator"], n_sub=2)))     # two substeps hold the bar again
+        env.reset()
+    assert env.fixed_step_probe_error < 1e-6
+
+
 @pytest.mark.parametrize("n", [65536, 20000])
 def test_default_adaptive_scheme_in_the_per_sm_kernel(n):
     """make_env's DEFAULT integrator (adaptive Tsit5, rtol = atol = 1e-8, the reference's jax path integrator.py:65-88)
