@@ -225,7 +225,9 @@ def ncu_traffic():
     """dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the headline kernel, from the newest committed ncu
     summary of it under profiles/ (one `ncu --set full` capture per kernel change; never a live counter)."""
     best = None
-    for f in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_cstr_*wsm*_ncu_summary.txt"))):
+    # captures of the SHIPPED fixed-step headline kernel, oldest first (the adaptive / general variants have their own files)
+    names = ["r1_cstr_v8_wsm_ncu_summary.txt", "r2_cstr_wsm_shipped_ncu_summary.txt", "r2_cstr_wsm_final_ncu_summary.txt"]
+    for f in [os.path.join(ROOT, "profiles", nme) for nme in names if os.path.exists(os.path.join(ROOT, "profiles", nme))]:
         txt = open(f).read()
         rd = re.search(r"DRAM read\s+([\d.]+)\s+(\w+)", txt)
         wr = re.search(r"DRAM written\s+([\d.]+)\s+(\w+)", txt)

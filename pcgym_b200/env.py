@@ -621,7 +621,9 @@ class make_env:
         def rows(v):                                      # per-env tables keep their first n rows
             a = v.detach().cpu().numpy() if isinstance(v, torch.Tensor) else np.asarray(v)
             return a[:n] if (a.ndim == 2 and a.shape[0] == self.n_envs and self.n_envs > 1) else a
-        base = {k: v for k, v in self.env_params.items() if k not in ("custom_reward", "integrator")}
+        # the probe compares states only: rewards and constraints (which may be Python callables rollout() cannot fuse) stay out
+        base = {k: v for k, v in self.env_params.items()
+                if k not in ("custom_reward", "integrator", "constraints", "done_on_cons_vio", "r_penalty", "cons_type")}
         base.update(n_envs=n, noise=False, device=str(self.device))
         if "x0" in base:
             base["x0"] = rows(base["x0"])
