@@ -114,6 +114,8 @@ enum pcg_flags {
   PCG_F_R_PENALTY = 1 << 3,     /* pcgym.py:556-557 / :529-530                      */
   PCG_F_DONE_ON_VIOLATION = 1 << 4, /* pcgym.py:613-614                             */
   PCG_F_ADAPTIVE = 1 << 5,      /* embedded error control (DOPRI5 / TSIT5 only)     */
+  PCG_F_EPISODE_START = 1 << 7, /* this launch begins an episode: io.done_state is NOT read (every env enters not
+                                   done), only written -- saves the caller a memset between back-to-back episodes  */
   PCG_F_SP_HIDDEN = 1 << 6      /* x0 / o_space carry no setpoint slots: the observation is [x] only while the
                                    reward still tracks SP (the reference's own custom-model test runs like this,
                                    tests/environment/test_make_env_custom_model.py:66-86; numpy lets the

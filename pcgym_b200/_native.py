@@ -43,7 +43,7 @@ NOISE = {"off": 0, "philox": 1, "external": 2, "philox_f32": 3}
 REWARD = {"none": 0, "sp": 1, "batch": 2, "ocp": 3}
 OCP_MOMENTS = 4                     # pcg_desc.ocp_mode bit (PCG_OCP_MOMENTS)
 
-F_NORMALISE_A, F_NORMALISE_O, F_A_DELTA, F_R_PENALTY, F_DONE_ON_VIOLATION, F_ADAPTIVE, F_SP_HIDDEN = (1 << i for i in range(7))
+F_NORMALISE_A, F_NORMALISE_O, F_A_DELTA, F_R_PENALTY, F_DONE_ON_VIOLATION, F_ADAPTIVE, F_SP_HIDDEN, F_EPISODE_START = (1 << i for i in range(8))
 ST_NONFINITE, ST_STEPCAP, ST_RANGE = 1, 2, 4
 
 f64, i32, u32, i64, u64 = C.c_double, C.c_int32, C.c_uint32, C.c_int64, C.c_uint64

@@ -78,7 +78,7 @@ fast_rollout_kernel(const __grid_constant__ pcg_desc d, const __grid_constant__ 
   }
   bool done[EPT];
 #pragma unroll
-  for (int e = 0; e < EPT; ++e) done[e] = io.done_state ? (io.done_state[env0 + e] != 0) : false;
+  for (int e = 0; e < EPT; ++e) done[e] = (io.done_state && !(flags & PCG_F_EPISODE_START)) ? (io.done_state[env0 + e] != 0) : false;
 
   const double* pa = io.a + env0;
   double* px = io.x_traj + env0;

@@ -402,7 +402,7 @@ rollout_kernel(const __grid_constant__ pcg_desc d, const __grid_constant__ pcg_i
   double h_carry[EPT];
 #pragma unroll
   for (int e = 0; e < EPT; ++e) {
-    done[e] = io.done_state ? (io.done_state[env0 + e] != 0) : false;
+    done[e] = (io.done_state && !(flags & PCG_F_EPISODE_START)) ? (io.done_state[env0 + e] != 0) : false;
     status[e] = 0;
     n_rhs[e] = 0;
     h_carry[e] = (ADAPTIVE && io.h_carry) ? io.h_carry[env0 + e] : 0.0;

@@ -82,7 +82,7 @@ lanes_rollout_kernel(const __grid_constant__ pcg_desc d, const __grid_constant__
     x[0] = io.x[static_cast<int64_t>(2 * s) * n + env];
     x[1] = io.x[static_cast<int64_t>(2 * s + 1) * n + env];
   }
-  bool done = (valid && io.done_state) ? (io.done_state[env] != 0) : false;
+  bool done = (valid && io.done_state && !(flags & PCG_F_EPISODE_START)) ? (io.done_state[env] != 0) : false;
   unsigned status = 0;
   int n_rhs = 0;
   double h = (valid && io.h_carry) ? io.h_carry[env] : 0.0;      // step size carried from interval to interval

@@ -229,7 +229,7 @@ ws_rollout_kernel(const __grid_constant__ pcg_desc d, const __grid_constant__ pc
 
   bool done[EPT];
 #pragma unroll
-  for (int e = 0; e < EPT; ++e) done[e] = io.done_state ? (io.done_state[env0 + e] != 0) : false;
+  for (int e = 0; e < EPT; ++e) done[e] = (io.done_state && !(d.flags & PCG_F_EPISODE_START)) ? (io.done_state[env0 + e] != 0) : false;
 
   double* px = io.x_traj + env0;
   double* po = io.obs + env0;

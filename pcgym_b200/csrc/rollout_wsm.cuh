@@ -350,7 +350,8 @@ wsm_rollout_kernel(const __grid_constant__ pcg_desc d, const __grid_constant__ p
         }
       }
     }
-    sh.done0[p][lane] = io.done_state ? *reinterpret_cast<const uchar2*>(io.done_state + env0) : make_uchar2(0, 0);
+    sh.done0[p][lane] = (io.done_state && !(d.flags & PCG_F_EPISODE_START)) ? *reinterpret_cast<const uchar2*>(io.done_state + env0)
+                                                                             : make_uchar2(0, 0);
     if (t0 == 0 && n_con > 0) {                                                // pcgym.py:416-420
       double x0[EPT][NX], uk0[EPT][NUK];
 #pragma unroll

@@ -127,6 +127,7 @@ class make_env:
             integ["adaptive"] = True
         self.integrator = integ
         self._fixed_checked = False
+        self._episode_fresh = False
         self.fixed_step_probe_error = None       # set by the first reset() of a fixed-step env (fixed_step_error)
 
         # pcgym.py:127-158
@@ -708,6 +709,7 @@ class make_env:
             self._a_save.copy_(self._a_save0)
         self._state0 = torch.cat(parts, dim=0)                                     # [n_obs, n]
         self._done_state.zero_()
+        self._episode_fresh = False
         self._status.zero_()
         self._h_carry.zero_()
         self._n_rhs.zero_()
@@ -1036,9 +1038,16 @@ class make_env:
             bufs = self._out_bufs(K, want_x)
         io = self._io(a, K, bufs, z)
         stream = torch.cuda.current_stream(self.device).cuda_stream
-        with torch.cuda.device(self.device):
-            nat.check(nat.lib().pcg_rollout(ctypes.byref(d), ctypes.byref(io), self.n_envs, self.t, K,
-                                            ctypes.c_void_p(stream)))
+        flags0 = d.flags
+        if self._episode_fresh:              # first launch after rewind(): the sticky done flag is not read (no memset needed)
+            d.flags = flags0 | nat.F_EPISODE_START
+        try:
+            with torch.cuda.device(self.device):
+                nat.check(nat.lib().pcg_rollout(ctypes.byref(d), ctypes.byref(io), self.n_envs, self.t, K,
+                                                ctypes.c_void_p(stream)))
+        finally:
+            d.flags = flags0
+        self._episode_fresh = False
         self.t += K
         if d.ocp_mode & 3 == 2:              # io.u_prev is valid from now on (it survives reset(), as `self.u_prev` does)
             self._desc.ocp_mode = self._desc_step.ocp_mode = (d.ocp_mode & ~3) | 1
@@ -1055,7 +1064,7 @@ class make_env:
             raise RuntimeError("call reset() before rewind()")
         self._begin_episode(episode)
         self.t = int(t)
-        self._done_state.zero_()
+        self._episode_fresh = True           # instead of a memset of the sticky done flag: PCG_F_EPISODE_START on the next launch
         self.done = False
         if to_x0:
             self._x.copy_(self._x_reset)
