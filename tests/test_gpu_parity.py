@@ -52,6 +52,10 @@ def test_step_cases_match_reference_fixture(name, golden_dir):
         assert isinstance(obs, np.ndarray) and isinstance(r, float) and isinstance(done, bool) and trunc is False
         np.testing.assert_allclose(env.state, g["state"][k], rtol=2e-8, atol=1e-11, err_msg=f"{name} state {k}")
         np.testing.assert_allclose(obs, g["obs"][k], rtol=5e-7, atol=5e-8, err_msg=f"{name} obs {k}")
+        # info["obs"] is the normalised observation BEFORE the partial-observation mask (pcgym.py:489 vs :495-498)
+        io_ = info["obs"]
+        io_ = io_.detach().cpu().numpy() if isinstance(io_, torch.Tensor) else np.asarray(io_)
+        np.testing.assert_allclose(io_.reshape(-1), g["info_obs"][k], rtol=5e-7, atol=5e-8, err_msg=f"{name} info obs {k}")
         np.testing.assert_allclose(r, g["reward"][k], rtol=1e-6, atol=1e-9, err_msg=f"{name} reward {k}")
         assert done == bool(g["done"][k]), f"{name} done {k}"
         if env.a_delta:
