@@ -285,6 +285,21 @@ int pcg_rollout(const pcg_desc* d, const pcg_io* io, int64_t n_env, int64_t t0, 
 int pcg_normal_pairs(const uint32_t* w0, const uint32_t* w1, double* z0, double* z1, int64_t n, int f32,
                      void* cuda_stream);
 
+/* The branch-free fp64 helpers the model right-hand sides use instead of the CUDA library's exp / log / sqrt / divide
+ * (csrc/fastmath.cuh), in isolation: y[i] = f(x[i]) for i < n, device pointers.  Lets a caller pin their accuracy
+ * (tests: <= 2 ulp against the correctly rounded value over the ranges the models use). */
+enum pcg_math_op {
+  PCG_MATH_EXP = 0,         /* exp_sat: Estrin degree-10, saturating at 2^+-1000            */
+  PCG_MATH_EXP_HORNER = 1,  /* exp_sat_horner                                               */
+  PCG_MATH_EXP_TAB = 2,     /* exp_tab_split: 2^(j/256) table + degree-4 (integrator warps) */
+  PCG_MATH_LOG = 3,         /* log_tab: log|x|, 128-entry table + degree-7 log1p            */
+  PCG_MATH_SQRT = 4,        /* sqrt_fast: MUFU.RSQ64H + Goldschmidt + residual correction   */
+  PCG_MATH_RCP = 5,         /* rcp_nr: MUFU.RCP64H + two Newton steps                       */
+  PCG_MATH_RCP_O3 = 6,      /* rcp_o3: one third-order correction                           */
+  PCG_MATH_COUNT = 7
+};
+int pcg_math_probe(int op, const double* x, double* y, int64_t n, void* cuda_stream);
+
 /* Number of kernel launches issued by this library since load (diagnostics for bench.py). */
 int64_t pcg_launch_count(void);
 

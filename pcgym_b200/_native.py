@@ -105,6 +105,7 @@ SYMBOLS = {
     "pcg_step": (C.c_int, [C.POINTER(Desc), C.POINTER(IO), C.c_int64, C.c_int64, C.c_void_p]),
     "pcg_rollout": (C.c_int, [C.POINTER(Desc), C.POINTER(IO), C.c_int64, C.c_int64, C.c_int64, C.c_void_p]),
     "pcg_normal_pairs": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]),
+    "pcg_math_probe": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "pcg_launch_count": (C.c_int64, []),
     "pcg_strerror": (C.c_char_p, [C.c_int]),
     "pcg_last_cuda_error": (C.c_char_p, []),
@@ -112,6 +113,7 @@ SYMBOLS = {
     "pcg_set_kernel": (C.c_int, [C.c_int]),
 }
 
+MATH_OPS = {"exp": 0, "exp_horner": 1, "exp_tab": 2, "log": 3, "sqrt": 4, "rcp": 5, "rcp_o3": 6}
 KERNELS = {"auto": -1, "generic": 0, "fast": 1, "ws": 2, "wsm": 3, "fast_ept1": 4, "generic_ept1": 5, "lanes": 6}
 
 _lib = None

@@ -127,6 +127,24 @@ __global__ void normal_pairs_kernel(const uint32_t* w0, const uint32_t* w1, doub
   z1[i] = b;
 }
 
+// the branch-free fp64 helpers of fastmath.cuh on caller-supplied arguments (pcg_math_probe)
+__global__ void math_probe_kernel(int op, const double* x, double* y, int64_t n) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double v = x[i];
+  double r;
+  switch (op) {
+    case PCG_MATH_EXP: r = pcg::exp_sat(v); break;
+    case PCG_MATH_EXP_HORNER: r = pcg::exp_sat_horner(v); break;
+    case PCG_MATH_EXP_TAB: { double sc, po; pcg::exp_tab_split(v, pcg::kExp2Tab, sc, po); r = sc * po; break; }
+    case PCG_MATH_LOG: r = pcg::log_tab(v); break;
+    case PCG_MATH_SQRT: r = pcg::sqrt_fast(v); break;
+    case PCG_MATH_RCP: r = pcg::rcp_nr(v); break;
+    default: r = pcg::rcp_o3(v); break;
+  }
+  y[i] = r;
+}
+
 std::atomic<int64_t> g_launches{0};
 thread_local char t_cuda_err[256] = "";
 
@@ -238,6 +256,20 @@ int pcg_normal_pairs(const uint32_t* w0, const uint32_t* w1, double* z0, double*
   if (n < 1 || n > (int64_t{1} << 31) - 256) return PCG_E_RANGE;
   const unsigned grid = static_cast<unsigned>((n + 255) / 256);
   normal_pairs_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(cuda_stream)>>>(w0, w1, z0, z1, n, f32 != 0);
+  const cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    std::strncpy(t_cuda_err, cudaGetErrorString(e), sizeof(t_cuda_err) - 1);
+    return PCG_E_CUDA;
+  }
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return PCG_OK;
+}
+
+int pcg_math_probe(int op, const double* x, double* y, int64_t n, void* cuda_stream) {
+  if (!x || !y) return PCG_E_NULL;
+  if (op < 0 || op >= PCG_MATH_COUNT || n < 1 || n > (int64_t{1} << 31) - 256) return PCG_E_RANGE;
+  const unsigned grid = static_cast<unsigned>((n + 255) / 256);
+  math_probe_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(cuda_stream)>>>(op, x, y, n);
   const cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     std::strncpy(t_cuda_err, cudaGetErrorString(e), sizeof(t_cuda_err) - 1);

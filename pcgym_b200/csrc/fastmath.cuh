@@ -48,7 +48,9 @@ PCG_DEV int exp_n_sat(double t) {
   return max(-1000, min(1000, n));
 }
 
-// exp(x), saturating at 2^+-1000 instead of overflowing, NaN-propagating.
+// exp(x), saturating at 2^+-1000 instead of overflowing, NaN-propagating.  (Saturation holds while x log2 e fits the
+// shifted double, |x| < ~1.5e9; further out the reduced argument is meaningless and the result is inf or NaN -- never a
+// finite wrong value, so a state that far gone still reaches the non-finite status check.  test: pcg_math_probe.)
 // n = rint(x log2 e) by the 1.5*2^52 shift, r = x - n ln2 (two-part ln2), degree-10 near-minimax polynomial
 // in Estrin form (dependency depth 4 instead of Horner's 10), scaled by 2^n built in the exponent field.
 PCG_DEV double exp_sat(double x) {
