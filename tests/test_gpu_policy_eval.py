@@ -36,14 +36,15 @@ def reference_rollout(params, policy):
     total_reward = []
     s = np.zeros((env.Nx, env.N))
     acts = np.zeros((alo.shape[0], env.N))
+    partial = bool(params.get("partial_observation"))
     o, info = env.reset()
     total_reward.append(info["r_init"])
-    s[:, 0] = (o + 1) * (hi - lo) / 2 + lo
+    s[:, 0] = ((info["obs"] if partial else o) + 1) * (hi - lo) / 2 + lo          # policy_evaluation.py:90-98
     for i in range(env.N - 1):
         a, _ = policy.predict(o, deterministic=True)
         o, r, term, trunc, info = env.step(a)
         acts[:, i] = (a + 1) * (ahi - alo) / 2 + alo
-        s[:, i + 1] = (o + 1) * (hi - lo) / 2 + lo
+        s[:, i + 1] = ((info["obs"] if partial else o) + 1) * (hi - lo) / 2 + lo   # policy_evaluation.py:107-114
         total_reward.append(r)
     cons = info["cons_info"] if env.constraint_active else np.zeros((1, env.N, 1))
     a, _ = policy.predict(o, deterministic=True)
@@ -75,6 +76,31 @@ def test_get_rollouts_matches_reference_loop_shapes_and_values():
             np.testing.assert_allclose(d["r"][0, :, k], r_ref, rtol=1e-5, atol=1e-9)
             np.testing.assert_allclose(d["g"][:, :, :, k], g_ref, rtol=1e-6, atol=1e-7)
     assert ev.data is data
+
+
+def test_get_rollouts_with_partial_observation_records_the_full_state():
+    """partial_observation hides states from the POLICY (the returned observation has them zeroed, pcgym.py:495-498),
+    but the rollout collector records the full state from info["obs"] (policy_evaluation.py:94-98, 110-114): the hidden
+    state's trajectory in data["x"] is the real one, not the observation-space midpoint (round-1 ADVICE)."""
+    from pcgym_b200 import make_env, policy_eval
+
+    class TP:                                                  # acts on the temperature: Ca is hidden from it
+        def predict(self, obs, deterministic=True):
+            o = np.asarray(obs, dtype=np.float64)
+            return np.clip(-3.0 * o[..., 1:2], -1, 1), None
+
+    p = cases.cstr_one_dist()
+    assert p["partial_observation"] == ["Ca"]
+    p.update(noise=False, integrator=TIGHT)
+    r_ref, s_ref, a_ref, _ = reference_rollout(p, TP())
+    assert np.ptp(s_ref[0]) > 1e-3                             # the hidden state moves
+    reps = 3
+    data = policy_eval(make_env, {"host": TP(), "dev": lambda obs: torch.clamp(-3.0 * obs[:, 1:2], -1, 1)}, reps, p).get_rollouts()
+    for name in ("host", "dev"):
+        for k in range(reps):
+            np.testing.assert_allclose(data[name]["x"][:, :, k], s_ref, rtol=1e-6, atol=1e-9, err_msg=name)
+            np.testing.assert_allclose(data[name]["u"][:, :, k], a_ref, rtol=1e-6, atol=1e-9, err_msg=name)
+            np.testing.assert_allclose(data[name]["r"][0, :, k], r_ref, rtol=1e-5, atol=1e-9, err_msg=name)
 
 
 def test_cuda_graph_replay_equals_eager_and_repeats():
