@@ -386,6 +386,12 @@ cudaError_t launch_e(const pcg_desc& d, const pcg_io& io, int64_t n_env, int t0,
   return launch_one<M, TB, ADAPTIVE, GENERAL, 1>(d, io, n_env, t0, k_steps, s);
 }
 
+// the general variant's 16 instantiations live in their own translation unit per model (inst_<model>_gen.cu: parallel nvcc)
+template <class M>
+cudaError_t launch_wsm_general(const pcg_desc&, const pcg_io&, int64_t, int, int, cudaStream_t, int64_t, int);
+template <>
+cudaError_t launch_wsm_general<Cstr>(const pcg_desc&, const pcg_io&, int64_t, int, int, cudaStream_t, int64_t, int);   // inst_cstr_gen.cu
+
 template <class M, class TB, bool ADAPTIVE>
 cudaError_t launch_g(const pcg_desc& d, const pcg_io& io, int64_t n_env, int t0, int k_steps, cudaStream_t s) {
   if constexpr (!ADAPTIVE && M::FAST && M::EPT == 2 && M::WS > 0 && std::is_same<TB, Tsit5>::value) {   // one tableau: 16 instantiations
@@ -394,7 +400,7 @@ cudaError_t launch_g(const pcg_desc& d, const pcg_io& io, int64_t n_env, int t0,
     int tiles = 0;
     if ((req == PCG_KERNEL_AUTO || req == PCG_KERNEL_WSM) && ept_override() != 1 && vector_ok(io, n_env) &&
         d.env_id0 % 2 == 0 && wsm_gen_ok<M>(d, io, n_env, k_steps, &epc, &tiles))
-      return launch_wsm<typename M::WsmModel, TB, false, true>(d, io, n_env, t0, k_steps, s, epc, tiles);
+      return launch_wsm_general<M>(d, io, n_env, t0, k_steps, s, epc, tiles);
   }
   return (needs_general<M>(d) || io.theta != nullptr) ? launch_e<M, TB, ADAPTIVE, true>(d, io, n_env, t0, k_steps, s)
                              : launch_e<M, TB, ADAPTIVE, false>(d, io, n_env, t0, k_steps, s);
