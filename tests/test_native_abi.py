@@ -93,6 +93,10 @@ def test_argument_validation_codes():
     for rc in range(0, -9, -1):
         assert L.pcg_strerror(rc) not in (None, b"unknown status")
     assert L.pcg_step(ctypes.byref(_valid_desc()), ctypes.byref(nat.IO()), 8, 0, None) == -1
+    # the diagnostic entry points validate before they launch as well
+    assert L.pcg_math_probe(nat.MATH_OPS["log"], None, None, 8, None) == -1
+    assert L.pcg_math_probe(99, 0x1000, 0x2000, 8, None) == -6 and L.pcg_math_probe(0, 0x1000, 0x2000, 0, None) == -6
+    assert L.pcg_normal_pairs(None, None, None, None, 8, 0, None) == -1
     assert L.pcg_launch_count() == 0                       # nothing was launched by any of the above
     with pytest.raises(nat.NativeError):
         nat.check(-3)
@@ -103,4 +107,5 @@ def test_kernel_request_knob():
     assert L.pcg_set_kernel(nat.KERNELS["wsm"]) == nat.KERNELS["auto"]          # returns the previous request
     assert L.pcg_set_kernel(nat.KERNELS["auto"]) == nat.KERNELS["wsm"]
     assert L.pcg_set_kernel(7) == -6 and L.pcg_set_kernel(-2) == -6
+    assert L.pcg_set_kernel(nat.KERNELS["lanes"]) == nat.KERNELS["auto"] and L.pcg_set_kernel(nat.KERNELS["auto"]) == nat.KERNELS["lanes"]
     assert L.pcg_set_kernel(nat.KERNELS["auto"]) == nat.KERNELS["auto"]
