@@ -20,6 +20,13 @@ parity target (CVODES at its default tolerances is itself only ~1e-5 accurate).
                   one Tsit5 step per control interval is compared with this at
                   ~1e-12 (same scheme, different arithmetic order) and with the
                   converged solution at the north-star rtol 1e-6.
+  advance_adaptive the embedded pairs ("dopri5", "tsit5") WITH the kernels' step-size
+                  controller (Hairer/Norsett/Wanner II.4 integral controller, FSAL, step
+                  carried between intervals), one env at a time: the same-scheme check
+                  of make_env's DEFAULT integrator -- the stand-in for the reference's
+                  jax path, diffrax Tsit5 + PIDController(rtol 1e-8, atol 1e-8)
+                  (integrator.py:57-88), which is an integral controller as well
+                  (pcoeff = dcoeff = 0) -- including its count of right-hand sides.
   advance_rodas4  the RODAS4 Rosenbrock 4(3) method with step-size control and a
                   finite-difference Jacobian, one env at a time: the same-scheme
                   check of the kernels' stiff integrator (scheme "rodas4"), which
@@ -124,6 +131,61 @@ def advance_fixed(model, x, u, dt, p=None, scheme="tsit5", n_sub=1):
             if b != 0.0:
                 x = x + (h * b) * kj
     return x
+
+
+# error weights b - b_hat of the embedded fourth-order solutions, over the S stages and the FSAL stage f(x_new)
+TABLEAUS["dopri5"]["E"] = [71 / 57600, 0, -71 / 16695, 71 / 1920, -17253 / 339200, 22 / 525, -1 / 40]
+TABLEAUS["tsit5"]["E"] = [-0.00178001105222577714, -0.0008164344596567469, 0.007880878010261995, -0.1447110071732629,
+                          0.5823571654525552, -0.45808210592918697, 1 / 66]
+
+
+def advance_adaptive(model, x, u, dt, p=None, scheme="tsit5", rtol=1e-8, atol=1e-8, h0=None, max_steps=4096):
+    """x(dt) for ONE env by the embedded pair with the kernels' controller (csrc/rollout_kernel.cuh:
+    advance_adaptive_aux): err^2 = mean((e / (atol + rtol max(|x|, |x'|)))^2), accept if err <= 1,
+    h *= clamp(0.9 err^-1/5, 0.2, 10) (no growth right after a rejection), a truncated last step does not shrink the
+    carried step, the derivative at x_new is reused as the next first stage.  Returns (x, h_carry, n_rhs)."""
+    f = _as_fun(model, p)
+    tb = TABLEAUS[scheme]
+    x = np.asarray(x, dtype=np.float64).copy()
+    u = np.asarray(u, dtype=np.float64)
+    t, h = 0.0, (h0 if (h0 is not None and 0 < h0 < dt) else float(dt))
+    k0, n_rhs, steps, rejected = f(x, u), 1, 0, False
+    while t < dt:
+        steps += 1
+        if steps > max_steps:
+            raise RuntimeError("advance_adaptive: step cap")
+        left = dt - t
+        last = h >= left * (1 - 1e-12)
+        hh = left if last else h
+        k = [k0]
+        for row in tb["A"][1:]:
+            xi = x.copy()
+            for a, kj in zip(row, k):
+                if a != 0.0:
+                    xi = xi + (hh * a) * kj
+            k.append(f(xi, u))
+        xn = x.copy()
+        for b, kj in zip(tb["B"], k):
+            if b != 0.0:
+                xn = xn + (hh * b) * kj
+        kn = f(xn, u)
+        n_rhs += len(tb["B"])
+        err = sum(e * (hh * kj) for e, kj in zip(tb["E"], k + [kn]) if e != 0.0)
+        sc = atol + rtol * np.maximum(np.abs(x), np.abs(xn))
+        msq = float(np.mean((err / sc) ** 2))
+        grow = 0.9 * max(msq, 1e-30) ** -0.1 if np.isfinite(msq) else 0.2
+        if np.isfinite(msq) and msq <= 1.0:
+            t = dt if last else t + hh
+            x, k0 = xn, kn
+            hn = hh * min(1.0 if rejected else 10.0, grow)
+            h = max(h, hn) if last else hn
+            rejected = False
+        else:
+            h = hh * max(0.2, min(grow, 1.0))
+            rejected = True
+            if not h > 1e-14 * dt:
+                raise RuntimeError("advance_adaptive: step size underflow")
+    return x, h, n_rhs
 
 
 # RODAS4 (Hairer & Wanner, Solving ODEs II, sec. IV.7; coefficients of rodas.f), transformed form:

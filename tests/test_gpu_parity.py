@@ -705,6 +705,40 @@ def test_fixed_step_probe_warns_when_the_interval_is_too_long():
     assert env.fixed_step_probe_error < 1e-6
 
 
+@pytest.mark.parametrize("scheme", ["tsit5", "dopri5"])
+def test_adaptive_kernel_against_the_restated_controller(scheme):
+    """make_env's default integrator (embedded pair + step-size controller) against its numpy restatement
+    (oracle.integrate.advance_adaptive: same tableau, same controller, step carried between intervals): the kernel
+    evaluates the growth factor in fp32 and exp / 1/T by its own routines, so the step sequences agree to ~1e-7 in h and
+    the states far inside the tolerance both runs are held to; the right-hand-side counts agree env by env except where
+    an accept decision falls within rounding of err = 1."""
+    n, K = 64, 10
+    params = cases.cstr_basic()
+    params.update(noise=False, n_envs=n, integrator={"scheme": scheme, "adaptive": True, "rtol": 1e-8, "atol": 1e-8})
+    rng = np.random.default_rng(2)
+    x0 = np.array([0.8, 330.0, 0.85])[None] * (1 + 0.02 * rng.uniform(-1, 1, (n, 3)))
+    params["x0"] = x0
+    acts = rng.uniform(-1, 1, (K, 1, n))
+    env = _env(params)
+    env.reset()
+    out = env.rollout(torch.as_tensor(acts))
+    got_x = out["x"].cpu().numpy()
+    got_n = env.rhs_evaluations.cpu().numpy()
+    lo, hi = params["a_space"]["low"], params["a_space"]["high"]
+    same_count = 0
+    for i in range(8):
+        x, h, total = x0[i, :2].copy(), None, 0
+        for k in range(K):
+            u = np.array([(acts[k, 0, i] + 1) * (hi[0] - lo[0]) / 2 + lo[0], 350.0, 1.0])
+            x, h, nr = oint.advance_adaptive("cstr", x, u, 0.25, scheme=scheme, rtol=1e-8, atol=1e-8, h0=h)
+            total += nr
+            np.testing.assert_allclose(got_x[k, :, i], x, rtol=2e-8, atol=0, err_msg=f"env {i} interval {k}")
+        same_count += int(total == int(got_n[i]))
+        assert abs(total - int(got_n[i])) <= 12, (i, total, int(got_n[i]))      # at most two step decisions apart
+    assert same_count >= 6, same_count
+    assert int(env.status.max()) == 0
+
+
 @pytest.mark.parametrize("n", [65536, 20000])
 def test_default_adaptive_scheme_in_the_per_sm_kernel(n):
     """make_env's DEFAULT integrator (adaptive Tsit5, rtol = atol = 1e-8, the reference's jax path integrator.py:65-88)

@@ -74,6 +74,13 @@ def test_oracle_tableaus_match_the_kernel_tableaus(name, order):
     np.testing.assert_array_equal(A[S][:S], b)
 
 
+@pytest.mark.parametrize("name", ["dopri5", "tsit5"])
+def test_oracle_error_weights_match_the_kernel_tableaus(name):
+    from oracle.integrate import TABLEAUS
+    _, E = parse({"dopri5": "Dopri5", "tsit5": "Tsit5"}[name])
+    np.testing.assert_array_equal(np.array(TABLEAUS[name]["E"]), E)
+
+
 def parse_rodas4():
     src = open(os.path.join(ROOT, "pcgym_b200", "csrc", "tableaus.cuh")).read()
     body = src[src.index("struct Rodas4"):]
